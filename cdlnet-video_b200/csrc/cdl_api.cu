@@ -1,0 +1,543 @@
+// cdl_api.cu — C ABI of libcdl_b200.so (declared in include/cdl_b200.h).
+//
+// Host-side orchestration of the reference's forward pass (model/net.py:76-92, 192-212, 659-675):
+//   preprocess -> [analysis_0] -> K-1 x [synthesis+residual ; analysis+update+ST] -> synthesis(D) -> postprocess
+// Every arithmetic step runs in a hand-written sm_100a kernel; there is no CPU or library fallback.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/cdl_b200.h"
+#include "cdl_cc.cuh"
+#include "cdl_common.cuh"
+#include "cdl_prepost.cuh"
+
+using namespace cdl;
+
+namespace {
+
+typedef void (*ana_fn_t)(const AnaParams);
+typedef void (*syn_fn_t)(const SynParams);
+
+struct Offsets {   // byte offsets into the caller's workspace
+  size_t rbuf, partial, sums, yp, mask_p, mean, xphat, end;
+  size_t h_y, h_mask, h_c, h_xhat, h_z, h_end;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct cdl_plan {
+  cdl_desc_t desc;
+  Geo g;
+  cdl_layout_t lay;
+  int precision_eff;
+  // CUDA-core path configuration
+  int MBT, MPAD, PWP;
+  ana_fn_t ana_fn;
+  syn_fn_t syn_fn;
+  int ana_TH, ana_TWS, ana_tiles_h, ana_tiles_w;
+  size_t ana_smem;
+  SynParams syn_cfg;   // geometry-dependent fields pre-filled
+  size_t syn_smem;
+  // device-resident packed filters / thresholds (owned by the plan)
+  float* wA;   // [K][C*T*MPAD]
+  float* wB;   // [K][M*C*Pd*Ph*PWP]
+  float* t;    // [K][2][M]
+  size_t wA_layer, wB_layer;
+  bool have_weights;
+  Offsets off;
+  uint64_t launches;
+};
+
+#define CDL_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return CDL_CUDA_ERROR_BASE + (int)e__; \
+  } while (0)
+
+#define CDL_LAUNCH_CHECK(plan)                           \
+  do {                                                   \
+    (plan)->launches++;                                  \
+    cudaError_t e__ = cudaGetLastError();                \
+    if (e__ != cudaSuccess) return CDL_CUDA_ERROR_BASE + (int)e__; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch tables
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <int S, int PW>
+ana_fn_t pick_ana_mbt(int MBT) {
+  switch (MBT) {
+    case 1: return k_cc_analysis<S, PW, 1>;
+    case 2: return k_cc_analysis<S, PW, 2>;
+    case 4: return k_cc_analysis<S, PW, 4>;
+    case 6: return k_cc_analysis<S, PW, 6>;
+    case 8: return k_cc_analysis<S, PW, 8>;
+  }
+  return nullptr;
+}
+template <int S>
+ana_fn_t pick_ana_pw(int PW, int MBT) {
+  switch (PW) {
+    case 3: return pick_ana_mbt<S, 3>(MBT);
+    case 5: return pick_ana_mbt<S, 5>(MBT);
+    case 7: return pick_ana_mbt<S, 7>(MBT);
+    case 9: return pick_ana_mbt<S, 9>(MBT);
+  }
+  return nullptr;
+}
+ana_fn_t pick_ana(int S, int PW, int MBT) {
+  if (S == 1) return pick_ana_pw<1>(PW, MBT);
+  if (S == 2) return pick_ana_pw<2>(PW, MBT);
+  return nullptr;
+}
+template <int S, int PW>
+size_t ana_smem_for(const Geo& g, int TH, int TWS, int MBT) { return ana_smem_bytes<S, PW>(g, TH, TWS, MBT); }
+size_t ana_smem(int S, int PW, const Geo& g, int TH, int TWS, int MBT) {
+#define CDL_AS(SV, PV) if (S == SV && PW == PV) return ana_smem_for<SV, PV>(g, TH, TWS, MBT);
+  CDL_AS(1, 3) CDL_AS(1, 5) CDL_AS(1, 7) CDL_AS(1, 9) CDL_AS(2, 3) CDL_AS(2, 5) CDL_AS(2, 7) CDL_AS(2, 9)
+#undef CDL_AS
+  return 0;
+}
+
+template <int S, int PW, bool ND3>
+syn_fn_t pick_syn_c(int C) {
+  switch (C) {
+    case 1: return k_cc_synthesis<S, PW, 1, ND3>;
+    case 2: return k_cc_synthesis<S, PW, 2, ND3>;
+    case 3: return k_cc_synthesis<S, PW, 3, ND3>;
+  }
+  return nullptr;
+}
+template <int S, bool ND3>
+syn_fn_t pick_syn_pw(int PW, int C) {
+  switch (PW) {
+    case 3: return pick_syn_c<S, 3, ND3>(C);
+    case 5: return pick_syn_c<S, 5, ND3>(C);
+    case 7: return pick_syn_c<S, 7, ND3>(C);
+    case 9: return pick_syn_c<S, 9, ND3>(C);
+  }
+  return nullptr;
+}
+syn_fn_t pick_syn(int S, int PW, int C, bool nd3) {
+  if (S == 1) return nd3 ? pick_syn_pw<1, true>(PW, C) : pick_syn_pw<1, false>(PW, C);
+  if (S == 2) return nd3 ? pick_syn_pw<2, true>(PW, C) : pick_syn_pw<2, false>(PW, C);
+  return nullptr;
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// pad L up to a multiple of s, the odd unit on the far side (model/utils.py:35-44)
+void calc_pad_1d(int L, int s, int* lo, int* hi) {
+  if (L % s == 0) { *lo = 0; *hi = 0; return; }
+  int diff = ceil_div(L, s) * s - L;
+  *lo = diff / 2; *hi = diff - diff / 2;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+extern "C" int cdl_abi_version(void) { return CDL_ABI_VERSION; }
+
+extern "C" const char* cdl_status_string(int s) {
+  switch (s) {
+    case CDL_OK: return "ok";
+    case CDL_ERR_NULL: return "null pointer argument";
+    case CDL_ERR_SHAPE: return "invalid or inconsistent shape";
+    case CDL_ERR_UNSUPPORTED: return "configuration not supported by any kernel";
+    case CDL_ERR_ALIGN: return "pointer not 16-byte aligned";
+    case CDL_ERR_NO_WEIGHTS: return "cdl_set_weights has not been called";
+    case CDL_ERR_NO_DEVICE: return "no usable CUDA device";
+    case CDL_ERR_RANGE: return "index out of range";
+    case CDL_ERR_WORKSPACE: return "workspace missing or too small";
+  }
+  if (s >= CDL_CUDA_ERROR_BASE) return cudaGetErrorString((cudaError_t)(s - CDL_CUDA_ERROR_BASE));
+  return "unknown status";
+}
+
+extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
+  if (!out || !d) return CDL_ERR_NULL;
+  *out = nullptr;
+  if (d->ndim != 2 && d->ndim != 3) return CDL_ERR_SHAPE;
+  const bool nd3 = d->ndim == 3;
+  if (d->N < 1 || d->C < 1 || d->M < 1 || d->K < 1 || d->s < 1) return CDL_ERR_SHAPE;
+  const int D = nd3 ? d->dims[0] : 1, H = d->dims[1], W = d->dims[2];
+  const int Pd = nd3 ? d->P[0] : 1, Ph = d->P[1], Pw = d->P[2];
+  if (D < 1 || H < 1 || W < 1 || Pd < 1 || Ph < 1 || Pw < 1) return CDL_ERR_SHAPE;
+  if (!(Pd & 1) || !(Ph & 1) || !(Pw & 1)) return CDL_ERR_UNSUPPORTED;   // padding P//2 is an adjoint pair only for odd P
+  if (d->halo_front < 0 || d->halo_back < 0 || ((d->halo_front || d->halo_back) && !nd3)) return CDL_ERR_SHAPE;
+  if (d->s > 2 || d->C > 3 || d->M > 256) return CDL_ERR_UNSUPPORTED;
+  if (Pw != 3 && Pw != 5 && Pw != 7 && Pw != 9) return CDL_ERR_UNSUPPORTED;
+  if (d->N > 65535) return CDL_ERR_UNSUPPORTED;
+
+  cdl_plan* p = new (std::nothrow) cdl_plan();
+  if (!p) return CDL_CUDA_ERROR_BASE + (int)cudaErrorMemoryAllocation;
+  memset(p, 0, sizeof(*p));
+  p->desc = *d;
+  const int s = d->s;
+  const bool slab = d->halo_front || d->halo_back;
+
+  // ---- index layout (bit-exact with calc_pad_2D / calc_pad_3D) ----
+  cdl_layout_t& L = p->lay;
+  calc_pad_1d(W, s, &L.pad[0], &L.pad[1]);
+  calc_pad_1d(H, s, &L.pad[2], &L.pad[3]);
+  if (nd3 && !slab) calc_pad_1d(D, s, &L.pad[4], &L.pad[5]); else { L.pad[4] = 0; L.pad[5] = 0; }
+  L.fine[0] = D + L.pad[4] + L.pad[5];
+  L.fine[1] = H + L.pad[2] + L.pad[3];
+  L.fine[2] = W + L.pad[0] + L.pad[1];
+  const int sd = nd3 ? s : 1;
+  if (slab) {
+    int owned = D - d->halo_front - d->halo_back;
+    if (owned < sd || owned % sd) { delete p; return CDL_ERR_SHAPE; }
+    if (d->halo_front > Pd / 2 || d->halo_back > Pd / 2) { delete p; return CDL_ERR_SHAPE; }
+    L.coarse[0] = owned / sd;
+  } else {
+    L.coarse[0] = L.fine[0] / sd;
+  }
+  L.coarse[1] = L.fine[1] / s;
+  L.coarse[2] = L.fine[2] / s;
+  // reflect padding needs pad < extent
+  if (L.pad[1] >= W || L.pad[3] >= H || (nd3 && L.pad[5] >= D && L.pad[5] > 0)) { delete p; return CDL_ERR_SHAPE; }
+
+  Geo& g = p->g;
+  g.N = d->N; g.C = d->C; g.M = d->M; g.K = d->K;
+  g.Fd = L.fine[0]; g.Fh = L.fine[1]; g.Fw = L.fine[2];
+  g.Qd = L.coarse[0]; g.Qh = L.coarse[1]; g.Qw = L.coarse[2];
+  g.Pd = Pd; g.Ph = Ph; g.Pw = Pw;
+  g.sd = sd; g.s = s;
+  g.od = Pd / 2 - d->halo_front; g.oh = Ph / 2; g.ow = Pw / 2;
+  g.ndim = d->ndim;
+  if (g.Qd > 65535) { delete p; return CDL_ERR_UNSUPPORTED; }
+
+  p->precision_eff = CDL_PREC_FP32;   // tensor-core kernels register themselves below when they cover the geometry
+
+  // ---- CUDA-core analysis configuration ----
+  const int mb = ceil_div(g.M, 32);
+  p->MBT = (mb <= 1) ? 1 : (mb <= 2) ? 2 : (mb <= 4) ? 4 : (mb <= 6) ? 6 : 8;
+  p->MPAD = 32 * p->MBT;
+  p->PWP = round_up(Pw, 4);
+  p->ana_fn = pick_ana(s, Pw, p->MBT);
+  p->syn_fn = pick_syn(s, Pw, g.C, nd3);
+  if (!p->ana_fn || !p->syn_fn) { delete p; return CDL_ERR_UNSUPPORTED; }
+  {
+    int TWS = (g.Qw <= 8) ? 1 : 2;
+    int TH = 8 / TWS;
+    const int nph = next_pow2(g.Qh);
+    if (TH > nph) TH = nph;          // few coarse rows: spend the warps along w instead
+    TWS = 8 / TH;
+    p->ana_TWS = TWS; p->ana_TH = TH;
+    p->ana_tiles_h = ceil_div(g.Qh, p->ana_TH);
+    p->ana_tiles_w = ceil_div(g.Qw, TWS * kAnaJB);
+    p->ana_smem = ana_smem(s, Pw, g, p->ana_TH, p->ana_TWS, p->MBT);
+  }
+  // ---- CUDA-core synthesis configuration ----
+  {
+    SynParams& sp = p->syn_cfg;
+    sp.g = g;
+    const int JB = kSynFW / s;
+    const int strips = ceil_div(g.Fw, kSynFW);
+    const int cells_h = ceil_div(g.Fh, s), cells_d = ceil_div(g.Fd, sd);
+    int TWs = next_pow2(strips); if (TWs > 16) TWs = 16;
+    int TDc = (nd3 && cells_d >= 2) ? 2 : 1;
+    int THc = kSynThreads / (TWs * TDc);
+    int nph = next_pow2(cells_h);
+    if (THc > nph) THc = nph;
+    if (nd3) { while (TWs * THc * TDc * 2 <= kSynThreads && TDc * 2 <= next_pow2(cells_d)) TDc *= 2; }
+    sp.TDc = TDc; sp.THc = THc; sp.TWs = TWs;
+    sp.tiles_d = ceil_div(cells_d, TDc); sp.tiles_h = ceil_div(cells_h, THc); sp.tiles_w = ceil_div(strips, TWs);
+    auto cdiv_signed = [](int a, int b) { return -floor_div(-a, b); };
+    sp.lo_d = cdiv_signed(g.od - (Pd - 1), sd);
+    const int hi_d = floor_div(sd - 1 + g.od, sd);
+    sp.lo_h = cdiv_signed(g.oh - (Ph - 1), s);
+    const int hi_h = floor_div(s - 1 + g.oh, s);
+    sp.ZD = TDc + hi_d - sp.lo_d;
+    sp.ZH = THc + hi_h - sp.lo_h;
+    const int lo_w = -((Pw - 1 - Pw / 2) / s), hi_w = (kSynFW - 1 + Pw / 2) / s;
+    const int NV = (hi_w - lo_w + 1 + 3) / 4;
+    sp.ZWP = JB * (TWs - 1) + 4 * NV;
+    const int zsz = sp.ZD * sp.ZH * sp.ZWP + g.C * Pd * Ph * p->PWP;
+    int MCH = 20480 / zsz; if (MCH < 1) MCH = 1; if (MCH > 8) MCH = 8; if (MCH > g.M) MCH = g.M;
+    sp.MCH = MCH;
+    p->syn_smem = (size_t)(round_up(MCH * sp.ZD * sp.ZH * sp.ZWP, 4) + MCH * g.C * Pd * Ph * p->PWP) * sizeof(float);
+    if (p->syn_smem > 200 * 1024 || p->ana_smem > 200 * 1024) { delete p; return CDL_ERR_UNSUPPORTED; }
+    if ((long long)sp.tiles_d * sp.tiles_h * sp.tiles_w > 2147483647LL) { delete p; return CDL_ERR_UNSUPPORTED; }
+  }
+
+  // ---- device state ----
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= d->device || d->device < 0) { delete p; return CDL_ERR_NO_DEVICE; }
+  cudaError_t e = cudaSetDevice(d->device);
+  if (e != cudaSuccess) { delete p; return CDL_CUDA_ERROR_BASE + (int)e; }
+  const int T = g.taps();
+  p->wA_layer = (size_t)g.C * T * p->MPAD;
+  p->wB_layer = (size_t)g.M * g.C * Pd * Ph * p->PWP;
+  if ((e = cudaMalloc(&p->wA, p->wA_layer * g.K * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&p->wB, p->wB_layer * g.K * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&p->t, (size_t)g.K * 2 * g.M * sizeof(float))) != cudaSuccess) {
+    cdl_plan_destroy(p);
+    return CDL_CUDA_ERROR_BASE + (int)e;
+  }
+  if ((e = cudaFuncSetAttribute((const void*)p->ana_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ana_smem)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute((const void*)p->syn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->syn_smem)) != cudaSuccess) {
+    cdl_plan_destroy(p);
+    return CDL_CUDA_ERROR_BASE + (int)e;
+  }
+
+  // ---- workspace layout ----
+  {
+    Offsets& o = p->off;
+    const size_t fine_bytes = (size_t)g.N * g.C * g.fine_vol() * sizeof(float);
+    const size_t in_bytes = (size_t)g.N * g.C * D * H * W * sizeof(float);
+    const size_t z_bytes = (size_t)g.N * g.M * g.coarse_vol() * sizeof(float);
+    size_t cur = 0;
+    o.rbuf = cur; cur = align_up(cur + fine_bytes, 256);
+    o.partial = cur; cur = align_up(cur + (size_t)g.N * 2 * kRedBlocksPerSample * sizeof(double), 256);
+    o.sums = cur; cur = align_up(cur + (size_t)g.N * 2 * sizeof(double), 256);
+    o.yp = cur; cur = align_up(cur + fine_bytes, 256);
+    o.mask_p = cur; cur = align_up(cur + (d->has_mask ? fine_bytes : 0), 256);
+    o.mean = cur; cur = align_up(cur + (size_t)g.N * sizeof(float), 256);
+    o.xphat = cur; cur = align_up(cur + fine_bytes, 256);
+    o.end = cur;
+    o.h_y = cur; cur = align_up(cur + in_bytes, 256);
+    o.h_mask = cur; cur = align_up(cur + (d->has_mask ? in_bytes : 0), 256);
+    o.h_c = cur; cur = align_up(cur + (size_t)g.N * sizeof(float), 256);
+    o.h_xhat = cur; cur = align_up(cur + in_bytes, 256);
+    o.h_z = cur; cur = align_up(cur + z_bytes, 256);
+    o.h_end = cur;
+  }
+  *out = p;
+  return CDL_OK;
+}
+
+extern "C" void cdl_plan_destroy(cdl_plan_t* p) {
+  if (!p) return;
+  if (p->wA) cudaFree(p->wA);
+  if (p->wB) cudaFree(p->wB);
+  if (p->t) cudaFree(p->t);
+  delete p;
+}
+
+extern "C" int cdl_plan_layout(const cdl_plan_t* p, cdl_layout_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->lay;
+  return CDL_OK;
+}
+extern "C" int cdl_plan_workspace_bytes(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->off.end;
+  return CDL_OK;
+}
+extern "C" int cdl_plan_host_workspace_bytes(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->off.h_end;
+  return CDL_OK;
+}
+extern "C" int cdl_plan_precision(const cdl_plan_t* p) { return p ? p->precision_eff : CDL_ERR_NULL; }
+extern "C" int cdl_plan_launch_count(const cdl_plan_t* p, uint64_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->launches;
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float* const* B, const float* t, void* stream_) {
+  if (!p || !A || !B || !t) return CDL_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const Geo& g = p->g;
+  const int T = g.taps();
+  for (int k = 0; k < g.K; ++k) {
+    if (!A[k] || !B[k]) return CDL_ERR_NULL;
+    {
+      long long total = (long long)p->wA_layer;
+      int blocks = (int)((total + 255) / 256); if (blocks > 1024) blocks = 1024;
+      k_pack_analysis<<<blocks, 256, 0, st>>>(A[k], p->wA + (size_t)k * p->wA_layer, g.M, g.C, T, p->MPAD);
+      CDL_LAUNCH_CHECK(p);
+    }
+    {
+      long long total = (long long)p->wB_layer;
+      int blocks = (int)((total + 255) / 256); if (blocks > 1024) blocks = 1024;
+      k_pack_synthesis<<<blocks, 256, 0, st>>>(B[k], p->wB + (size_t)k * p->wB_layer, g.M * g.C * g.Pd * g.Ph, g.Pw, p->PWP);
+      CDL_LAUNCH_CHECK(p);
+    }
+  }
+  CDL_CUDA(cudaMemcpyAsync(p->t, t, (size_t)g.K * 2 * g.M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  p->have_weights = true;
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// preprocess / postprocess
+// ------------------------------------------------------------------------------------------------
+static PadParams pad_params(const cdl_plan* p) {
+  PadParams q;
+  const bool nd3 = p->desc.ndim == 3;
+  q.N = p->g.N; q.C = p->g.C;
+  q.D = nd3 ? p->desc.dims[0] : 1; q.H = p->desc.dims[1]; q.W = p->desc.dims[2];
+  q.Fd = p->g.Fd; q.Fh = p->g.Fh; q.Fw = p->g.Fw;
+  q.pf = p->lay.pad[4]; q.pt = p->lay.pad[2]; q.pl = p->lay.pad[0];
+  return q;
+}
+
+extern "C" int cdl_reduce_sums(cdl_plan_t* p, const float* y, const float* mask, double* sums, void* ws, void* stream_) {
+  if (!p || !y || !sums) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  if (p->desc.has_mask && !mask) return CDL_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream_;
+  PadParams q = pad_params(p);
+  const long long per = (long long)q.C * q.D * q.H * q.W;
+  double* partial = reinterpret_cast<double*>((char*)ws + p->off.partial);
+  dim3 grid(kRedBlocksPerSample, q.N);
+  k_reduce_partial<<<grid, kRedThreads, 0, st>>>(y, p->desc.has_mask ? mask : nullptr, partial, per);
+  CDL_LAUNCH_CHECK(p);
+  k_reduce_final<<<ceil_div(q.N, 128), 128, 0, st>>>(partial, sums, kRedBlocksPerSample, q.N, p->desc.has_mask, (double)per);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+extern "C" int cdl_mean_from_sums(cdl_plan_t* p, const double* sums, float* mean, void* stream_) {
+  if (!p || !sums || !mean) return CDL_ERR_NULL;
+  k_mean_from_sums<<<ceil_div(p->g.N, 128), 128, 0, (cudaStream_t)stream_>>>(sums, mean, p->g.N);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+extern "C" int cdl_center_pad(cdl_plan_t* p, const float* y, const float* mask, const float* mean, float* yp, float* mask_p, void* stream_) {
+  if (!p || !y || !mean || !yp) return CDL_ERR_NULL;
+  if (p->desc.has_mask && (!mask || !mask_p)) return CDL_ERR_NULL;
+  PadParams q = pad_params(p);
+  const long long total = (long long)q.N * q.C * q.Fd * q.Fh * q.Fw;
+  long long blocks = (total + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+  k_center_pad<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(y, p->desc.has_mask ? mask : nullptr, mean, yp, mask_p, q);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+extern "C" int cdl_preprocess(cdl_plan_t* p, const float* y, const float* mask, float* yp, float* mask_p, float* mean, void* ws, void* stream_) {
+  if (!p || !mean) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  double* sums = reinterpret_cast<double*>((char*)ws + p->off.sums);
+  int rc = cdl_reduce_sums(p, y, mask, sums, ws, stream_);
+  if (rc) return rc;
+  rc = cdl_mean_from_sums(p, sums, mean, stream_);
+  if (rc) return rc;
+  return cdl_center_pad(p, y, mask, mean, yp, mask_p, stream_);
+}
+
+extern "C" int cdl_postprocess(cdl_plan_t* p, const float* xphat, const float* mean, float* xhat, void* stream_) {
+  if (!p || !xphat || !mean || !xhat) return CDL_ERR_NULL;
+  PadParams q = pad_params(p);
+  const long long total = (long long)q.N * q.C * q.D * q.H * q.W;
+  long long blocks = (total + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+  k_unpad_add_mean<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(xphat, mean, xhat, q);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ISTA steps
+// ------------------------------------------------------------------------------------------------
+extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, void* ws, void* stream_) {
+  (void)ws;
+  if (!p || !r || !z) return CDL_ERR_NULL;
+  if (!p->have_weights) return CDL_ERR_NO_WEIGHTS;
+  if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
+  if ((reinterpret_cast<uintptr_t>(z) & 15) || (reinterpret_cast<uintptr_t>(r) & 15)) return CDL_ERR_ALIGN;
+  AnaParams a;
+  a.g = p->g;
+  a.rin = r; a.z = z;
+  a.wA = p->wA + (size_t)k * p->wA_layer;
+  a.t0 = p->t + (size_t)k * 2 * p->g.M;
+  a.t1 = a.t0 + p->g.M;
+  a.cvec = c;
+  a.first = first ? 1 : 0;
+  a.TH = p->ana_TH; a.TWS = p->ana_TWS; a.tiles_h = p->ana_tiles_h; a.tiles_w = p->ana_tiles_w;
+  dim3 grid(a.tiles_h * a.tiles_w, p->g.Qd, p->g.N);
+  p->ana_fn<<<grid, kAnaThreads, p->ana_smem, (cudaStream_t)stream_>>>(a);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const float* z, const float* yp, const float* mask_p, float* out, void* ws, void* stream_) {
+  (void)ws;
+  if (!p || !z || !out) return CDL_ERR_NULL;
+  if (residual && !yp) return CDL_ERR_NULL;
+  if (residual && p->desc.has_mask && !mask_p) return CDL_ERR_NULL;
+  if (!p->have_weights) return CDL_ERR_NO_WEIGHTS;
+  if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
+  if ((reinterpret_cast<uintptr_t>(z) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (yp && (reinterpret_cast<uintptr_t>(yp) & 15)) || (mask_p && (reinterpret_cast<uintptr_t>(mask_p) & 15))) return CDL_ERR_ALIGN;
+  SynParams s = p->syn_cfg;
+  s.z = z;
+  s.wB = p->wB + (size_t)k * p->wB_layer;
+  s.yp = residual ? yp : nullptr;
+  s.mask = (residual && p->desc.has_mask) ? mask_p : nullptr;
+  s.out = out;
+  s.residual = residual ? 1 : 0;
+  dim3 grid(s.tiles_d * s.tiles_h * s.tiles_w, p->g.N);
+  p->syn_fn<<<grid, kSynThreads, p->syn_smem, (cudaStream_t)stream_>>>(s);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+extern "C" int cdl_forward(cdl_plan_t* p, const float* yp, const float* mask_p, const float* c, float* z, float* xphat, void* ws, void* stream_) {
+  if (!p || !yp || !z || !xphat) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  float* rbuf = reinterpret_cast<float*>((char*)ws + p->off.rbuf);
+  int rc = cdl_analysis_step(p, 0, 1, yp, c, z, ws, stream_);                      // model/net.py:85,200
+  for (int k = 1; k < p->g.K && !rc; ++k) {                                        // model/net.py:86-87,204-205
+    rc = cdl_synthesis_step(p, k, 1, z, yp, mask_p, rbuf, ws, stream_);
+    if (!rc) rc = cdl_analysis_step(p, k, 0, rbuf, c, z, ws, stream_);
+  }
+  if (!rc) rc = cdl_synthesis_step(p, 0, 0, z, nullptr, nullptr, xphat, ws, stream_);   // D = B[0], model/net.py:90,210
+  return rc;
+}
+
+extern "C" int cdl_denoise(cdl_plan_t* p, const float* y, const float* mask, const float* c, float* xhat, float* z, void* ws, void* stream_) {
+  if (!p || !y || !xhat || !z) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  char* w = (char*)ws;
+  float* yp = reinterpret_cast<float*>(w + p->off.yp);
+  float* mask_p = p->desc.has_mask ? reinterpret_cast<float*>(w + p->off.mask_p) : nullptr;
+  float* mean = reinterpret_cast<float*>(w + p->off.mean);
+  float* xphat = reinterpret_cast<float*>(w + p->off.xphat);
+  int rc = cdl_preprocess(p, y, mask, yp, mask_p, mean, ws, stream_);
+  if (!rc) rc = cdl_forward(p, yp, mask_p, c, z, xphat, ws, stream_);
+  if (!rc) rc = cdl_postprocess(p, xphat, mean, xhat, stream_);
+  return rc;
+}
+
+extern "C" int cdl_denoise_host(cdl_plan_t* p, const float* y_host, const float* mask_host, const float* c_host,
+                                float* xhat_host, float* z_host, void* ws, void* stream_) {
+  if (!p || !y_host || !xhat_host) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  if (p->desc.has_mask && !mask_host) return CDL_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream_;
+  char* w = (char*)ws;
+  const Geo& g = p->g;
+  const bool nd3 = p->desc.ndim == 3;
+  const size_t in_bytes = (size_t)g.N * g.C * (nd3 ? p->desc.dims[0] : 1) * p->desc.dims[1] * p->desc.dims[2] * sizeof(float);
+  const size_t z_bytes = (size_t)g.N * g.M * g.coarse_vol() * sizeof(float);
+  float* y = reinterpret_cast<float*>(w + p->off.h_y);
+  float* mask = p->desc.has_mask ? reinterpret_cast<float*>(w + p->off.h_mask) : nullptr;
+  float* c = c_host ? reinterpret_cast<float*>(w + p->off.h_c) : nullptr;
+  float* xhat = reinterpret_cast<float*>(w + p->off.h_xhat);
+  float* z = reinterpret_cast<float*>(w + p->off.h_z);
+  CDL_CUDA(cudaMemcpyAsync(y, y_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if (mask) CDL_CUDA(cudaMemcpyAsync(mask, mask_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if (c) CDL_CUDA(cudaMemcpyAsync(c, c_host, (size_t)g.N * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = cdl_denoise(p, y, mask, c, xhat, z, ws, stream_);
+  if (rc) return rc;
+  CDL_CUDA(cudaMemcpyAsync(xhat_host, xhat, in_bytes, cudaMemcpyDeviceToHost, st));
+  if (z_host) CDL_CUDA(cudaMemcpyAsync(z_host, z, z_bytes, cudaMemcpyDeviceToHost, st));
+  return CDL_OK;
+}

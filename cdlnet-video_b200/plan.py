@@ -1,0 +1,178 @@
+"""Host-side handle on a `cdl_plan_t` (include/cdl_b200.h): geometry, packed filters, workspace.
+
+PyTorch is used only for device memory and streams: every tensor handed to the library is a
+contiguous fp32 CUDA tensor whose `data_ptr()` is passed through ctypes.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PREC = {"fp32": 0, "tf32": 1}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plan:
+    """One geometry: (ndim, N, C, M, K, dims, P, s, mask?, precision[, temporal halos]) on one device."""
+
+    def __init__(self, ndim, N, C, M, K, dims, P, s, has_mask=False, precision="fp32", device=0,
+                 halo_front=0, halo_back=0):
+        self.lib = _lib.load()
+        d = _lib.CdlDesc()
+        d.ndim, d.N, d.C, d.M, d.K, d.s = ndim, N, C, M, K, s
+        dims3 = (1, *dims) if ndim == 2 else tuple(dims)
+        P3 = (1, *P) if ndim == 2 else tuple(P)
+        for i in range(3):
+            d.dims[i] = int(dims3[i])
+            d.P[i] = int(P3[i])
+        d.has_mask = int(bool(has_mask))
+        d.precision = PREC[precision] if isinstance(precision, str) else int(precision)
+        d.halo_front, d.halo_back, d.device = int(halo_front), int(halo_back), int(device)
+        self.desc = d
+        self.device = torch.device("cuda", int(device))
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.cdl_plan_create(ctypes.byref(handle), ctypes.byref(d)), "cdl_plan_create")
+        self.handle = handle
+        lay = _lib.CdlLayout()
+        _lib.check(self.lib.cdl_plan_layout(handle, ctypes.byref(lay)), "cdl_plan_layout")
+        self.pad = tuple(lay.pad)                    # (l, r, t, b, f, k)
+        self.fine = tuple(lay.fine)                  # padded (D,H,W)
+        self.coarse = tuple(lay.coarse)              # z (D,H,W)
+        self.ndim, self.N, self.C, self.M, self.K, self.s = ndim, N, C, M, K, s
+        self.dims = tuple(int(v) for v in dims)
+        self.has_mask = bool(has_mask)
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.cdl_plan_workspace_bytes(handle, ctypes.byref(n)))
+        self.workspace_bytes = n.value
+        _lib.check(self.lib.cdl_plan_host_workspace_bytes(handle, ctypes.byref(n)))
+        self.host_workspace_bytes = n.value
+        self._ws = None
+        self._weights_key = None
+        self._keep = None
+
+    # shapes -------------------------------------------------------------------------------------
+    @property
+    def fine_shape(self):
+        return (self.N, self.C, *(self.fine if self.ndim == 3 else self.fine[1:]))
+
+    @property
+    def z_shape(self):
+        return (self.N, self.M, *(self.coarse if self.ndim == 3 else self.coarse[1:]))
+
+    @property
+    def in_shape(self):
+        return (self.N, self.C, *self.dims)
+
+    @property
+    def precision(self):
+        return {0: "fp32", 1: "tf32"}[self.lib.cdl_plan_precision(self.handle)]
+
+    def launch_count(self):
+        n = ctypes.c_uint64()
+        _lib.check(self.lib.cdl_plan_launch_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def workspace(self, host=False):
+        need = self.host_workspace_bytes if host else self.workspace_bytes
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cdl_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # weights ------------------------------------------------------------------------------------
+    def set_weights(self, A, B, t, key=None):
+        """A, B: K tensors (M,C,P...) fp32 CUDA; t: (K,2,M,...) fp32 CUDA."""
+        if key is not None and key == self._weights_key:
+            return
+        K = self.K
+        A = [a.detach().to(self.device, torch.float32).contiguous() for a in A]
+        B = [b.detach().to(self.device, torch.float32).contiguous() for b in B]
+        t = t.detach().to(self.device, torch.float32).reshape(K, 2, self.M).contiguous()
+        arrA = (ctypes.c_void_p * K)(*[a.data_ptr() for a in A])
+        arrB = (ctypes.c_void_p * K)(*[b.data_ptr() for b in B])
+        _lib.check(self.lib.cdl_set_weights(self.handle, arrA, arrB, _ptr(t), _stream()), "cdl_set_weights")
+        self._keep = (A, B, t)      # keep sources alive until the async repack has run
+        self._weights_key = key
+
+    # whole forward ------------------------------------------------------------------------------
+    def denoise(self, y, mask=None, c=None, z_out=None):
+        """y (N,C,dims) -> (xhat like y, z).  c: (N,) fp32 sigma/255 or None."""
+        xhat = torch.empty(self.in_shape, dtype=torch.float32, device=self.device)
+        z = z_out if z_out is not None else torch.empty(self.z_shape, dtype=torch.float32, device=self.device)
+        ws = self.workspace()
+        _lib.check(self.lib.cdl_denoise(self.handle, _ptr(y), _ptr(mask), _ptr(c), _ptr(xhat), _ptr(z), _ptr(ws), _stream()),
+                   "cdl_denoise")
+        return xhat, z
+
+    def denoise_host(self, y_host, xhat_host, mask_host=None, c_host=None, z_host=None):
+        """Pinned host buffers in, pinned host buffers out; asynchronous on the current stream."""
+        ws = self.workspace(host=True)
+        _lib.check(self.lib.cdl_denoise_host(self.handle, _ptr(y_host), _ptr(mask_host), _ptr(c_host), _ptr(xhat_host),
+                                             _ptr(z_host), _ptr(ws), _stream()), "cdl_denoise_host")
+
+    # stepwise API (forward_generator, temporal slabs) ----------------------------------------------
+    def preprocess(self, y, mask=None):
+        yp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device)
+        mp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device) if self.has_mask else None
+        mean = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cdl_preprocess(self.handle, _ptr(y), _ptr(mask), _ptr(yp), _ptr(mp), _ptr(mean),
+                                           _ptr(self.workspace()), _stream()), "cdl_preprocess")
+        return yp, mp, mean
+
+    def reduce_sums(self, y, mask=None):
+        sums = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.cdl_reduce_sums(self.handle, _ptr(y), _ptr(mask), _ptr(sums), _ptr(self.workspace()), _stream()),
+                   "cdl_reduce_sums")
+        return sums
+
+    def mean_from_sums(self, sums):
+        mean = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cdl_mean_from_sums(self.handle, _ptr(sums), _ptr(mean), _stream()), "cdl_mean_from_sums")
+        return mean
+
+    def center_pad(self, y, mean, mask=None):
+        yp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device)
+        mp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device) if self.has_mask else None
+        _lib.check(self.lib.cdl_center_pad(self.handle, _ptr(y), _ptr(mask), _ptr(mean), _ptr(yp), _ptr(mp), _stream()),
+                   "cdl_center_pad")
+        return yp, mp
+
+    def analysis_step(self, k, r, z, c=None, first=False):
+        _lib.check(self.lib.cdl_analysis_step(self.handle, k, int(first), _ptr(r), _ptr(c), _ptr(z),
+                                              _ptr(self.workspace()), _stream()), "cdl_analysis_step")
+        return z
+
+    def synthesis_step(self, k, z, out, yp=None, mask_p=None, residual=True):
+        _lib.check(self.lib.cdl_synthesis_step(self.handle, k, int(residual), _ptr(z), _ptr(yp), _ptr(mask_p), _ptr(out),
+                                               _ptr(self.workspace()), _stream()), "cdl_synthesis_step")
+        return out
+
+    def forward(self, yp, mask_p=None, c=None):
+        z = torch.empty(self.z_shape, dtype=torch.float32, device=self.device)
+        xp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cdl_forward(self.handle, _ptr(yp), _ptr(mask_p), _ptr(c), _ptr(z), _ptr(xp),
+                                        _ptr(self.workspace()), _stream()), "cdl_forward")
+        return z, xp
+
+    def postprocess(self, xp, mean):
+        xhat = torch.empty(self.in_shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cdl_postprocess(self.handle, _ptr(xp), _ptr(mean), _ptr(xhat), _stream()), "cdl_postprocess")
+        return xhat

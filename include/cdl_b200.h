@@ -1,0 +1,127 @@
+/* cdl_b200.h — C ABI of libcdl_b200.so: the CDLNet K-iteration ISTA forward pass on B200 (sm_100a).
+ *
+ * The reference (RQLuo/CDLNet-video) has no FFI layer: its hot path is the body of
+ *   CDLNet.forward        model/net.py:76-92
+ *   CDLNetVideo.forward   model/net.py:192-212
+ *   GDLNet.forward        model/net.py:659-675
+ * plus pre_process[_3d] / post_process[_3d] (model/utils.py:5-33, 70-98).  This header is the
+ * boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): plain pointers and sizes,
+ * no torch types.  All data pointers are DEVICE pointers to contiguous fp32 unless a name ends in
+ * `_host`.  The library never allocates or frees caller memory and never synchronises the device;
+ * work is enqueued on the `stream` argument (a cudaStream_t passed as void*).
+ *
+ * Return convention: 0 = OK; <0 = argument / shape / unsupported-configuration error (see the
+ * enum); >0 = a cudaError_t passed through + CDL_CUDA_ERROR_BASE.  Nothing is printed, nothing
+ * throws or aborts.
+ */
+#ifndef CDL_B200_H
+#define CDL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDL_ABI_VERSION 1
+#define CDL_CUDA_ERROR_BASE 1000
+
+enum cdl_status {
+  CDL_OK = 0,
+  CDL_ERR_NULL = -1,        /* a required pointer is NULL                                   */
+  CDL_ERR_SHAPE = -2,       /* non-positive / inconsistent extents                          */
+  CDL_ERR_UNSUPPORTED = -3, /* configuration has no kernel (even P, M > 256, ...)           */
+  CDL_ERR_ALIGN = -4,       /* pointer not 16-byte aligned                                  */
+  CDL_ERR_NO_WEIGHTS = -5,  /* cdl_set_weights has not been called                          */
+  CDL_ERR_NO_DEVICE = -6,   /* no CUDA device / not an sm_100 device                        */
+  CDL_ERR_RANGE = -7,       /* layer index or slab range out of bounds                      */
+  CDL_ERR_WORKSPACE = -8    /* workspace NULL or too small                                  */
+};
+
+enum cdl_precision {
+  CDL_PREC_FP32 = 0, /* CUDA-core fp32 FMA: same arithmetic class as the reference on CPU  */
+  CDL_PREC_TF32 = 1  /* tcgen05 kind::tf32, operands rounded RNE, fp32 accumulate in TMEM  */
+};
+
+/* Geometry of one plan.  Mirrors the constructor kwargs of the reference modules
+ * (model/net.py:20-28, 123-133, 572-582) plus the input extents.
+ *
+ * Temporal slabs (multi-GPU): a rank owning coarse frames [q0,q1) of a longer clip
+ * creates its plan with dims[0] = the number of fine frames it keeps resident (its own s*(q1-q0)
+ * frames plus `halo_front` frames before and `halo_back` after), and sets halo_front/halo_back
+ * (Pd/2 and Pd/2-s+1 at a seam, 0 at a true clip end).  With both 0 the plan is the ordinary
+ * unsharded operator with zero padding Pd/2 at both ends.                                        */
+typedef struct cdl_desc {
+  int32_t ndim;        /* 2 (images N,C,H,W) or 3 (clips N,C,D,H,W)                          */
+  int32_t N, C, M, K;  /* batch, image channels, subbands, unrolled iterations              */
+  int32_t dims[3];     /* UNPADDED input extents (D,H,W); D ignored (1) when ndim == 2       */
+  int32_t P[3];        /* filter extents (Pd,Ph,Pw), odd; Pd ignored (1) when ndim == 2      */
+  int32_t s;           /* stride                                                             */
+  int32_t has_mask;    /* 1: a mask tensor shaped like y multiplies B z (JDD, net.py:87)     */
+  int32_t precision;   /* enum cdl_precision                                                 */
+  int32_t halo_front;  /* temporal slab: extra fine frames held before the owned range       */
+  int32_t halo_back;   /* temporal slab: extra fine frames held after the owned range        */
+  int32_t device;      /* CUDA device ordinal                                                */
+} cdl_desc_t;
+
+typedef struct cdl_plan cdl_plan_t;
+
+/* Derived index layout, bit-exact with calc_pad_2D / calc_pad_3D (model/utils.py:35-51,100-108). */
+typedef struct cdl_layout {
+  int32_t pad[6];      /* (left,right,top,bottom,front,back) — the reference's tuple order   */
+  int32_t fine[3];     /* padded (D,H,W) of yp / residual / xphat                            */
+  int32_t coarse[3];   /* (D,H,W) of the sparse code z                                       */
+} cdl_layout_t;
+
+int         cdl_abi_version(void);
+const char* cdl_status_string(int status);
+
+int  cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* desc);
+void cdl_plan_destroy(cdl_plan_t* plan);
+int  cdl_plan_layout(const cdl_plan_t* plan, cdl_layout_t* out);
+int  cdl_plan_workspace_bytes(const cdl_plan_t* plan, size_t* out);
+/* Effective precision after plan creation (a TF32 request falls back to FP32 kernels for
+ * geometries the tensor-core path does not cover; never to the CPU).                          */
+int  cdl_plan_precision(const cdl_plan_t* plan);
+
+/* Filters and thresholds.  A[k], B[k]: K device pointers (HOST array of pointers) to the
+ * (M,C,Pd,Ph,Pw) weights of nn.Conv / nn.ConvTranspose (model/net.py:32-33,137-142) or to the
+ * synthesised Gabor filters (model/gabor.py:46-51).  t: (K,2,M) thresholds (model/net.py:35,144).
+ * Repacks into the kernels' layouts; call again after any weight change.                        */
+int cdl_set_weights(cdl_plan_t* plan, const float* const* A, const float* const* B, const float* t, void* stream);
+
+/* pre_process / pre_process_3d (model/utils.py:5-22, 70-87).
+ * sums: optional (2N) doubles out: per-sample sum(y), sum(mask) (or element count).             */
+int cdl_reduce_sums(cdl_plan_t* plan, const float* y, const float* mask, double* sums, void* workspace, void* stream);
+int cdl_mean_from_sums(cdl_plan_t* plan, const double* sums, float* mean, void* stream);
+int cdl_center_pad(cdl_plan_t* plan, const float* y, const float* mask, const float* mean, float* yp, float* mask_p, void* stream);
+int cdl_preprocess(cdl_plan_t* plan, const float* y, const float* mask, float* yp, float* mask_p, float* mean, void* workspace, void* stream);
+
+/* One analysis step  z <- ST(z_in -/+ A_k r, t[k,0] + c*t[k,1])   (model/net.py:85,87;200,205).
+ * first != 0: z <- ST(A_k r, .) with r = yp (iteration 0, no z_in).  In place on z.  c: N floats or NULL. */
+int cdl_analysis_step(cdl_plan_t* plan, int k, int first, const float* r, const float* c, float* z, void* workspace, void* stream);
+/* One synthesis step  out <- mask_p * B_k z - yp  (residual != 0) or out <- B_k z (residual == 0). */
+int cdl_synthesis_step(cdl_plan_t* plan, int k, int residual, const float* z, const float* yp, const float* mask_p, float* out, void* workspace, void* stream);
+
+/* All K iterations + D z:  z (N,M,coarse) and xphat (N,C,fine) out.                              */
+int cdl_forward(cdl_plan_t* plan, const float* yp, const float* mask_p, const float* c, float* z, float* xphat, void* workspace, void* stream);
+/* post_process / post_process_3d (model/utils.py:24-33, 89-98): crop the stride padding, add the mean. */
+int cdl_postprocess(cdl_plan_t* plan, const float* xphat, const float* mean, float* xhat, void* stream);
+
+/* pre + forward + post on device buffers: y, mask (N,C,dims) -> xhat (N,C,dims), z (N,M,coarse).   */
+int cdl_denoise(cdl_plan_t* plan, const float* y, const float* mask, const float* c, float* xhat, float* z, void* workspace, void* stream);
+/* Same with HOST buffers (pinned for true asynchrony): copies y/mask/c in, xhat (and z if z_host
+ * is non-NULL) out, on `stream`.  The device staging area lives in `workspace` (see
+ * cdl_plan_host_workspace_bytes).  This is the end-to-end entry bench.py's `e2e` times.            */
+int cdl_plan_host_workspace_bytes(const cdl_plan_t* plan, size_t* out);
+int cdl_denoise_host(cdl_plan_t* plan, const float* y_host, const float* mask_host, const float* c_host,
+                     float* xhat_host, float* z_host, void* workspace, void* stream);
+
+/* Number of kernels launched by this plan since creation (bench.py's gpu_launches).               */
+int cdl_plan_launch_count(const cdl_plan_t* plan, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDL_B200_H */

@@ -1,0 +1,184 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in modules) against the reference's golden
+outputs and against the CPU oracle on seeded inputs.
+
+Tolerances (stated per north_star): max-abs <= 1e-4 on xhat and PSNR within 0.01 dB for every kernel
+family; the exact fp32 family is held to 2e-5.  Padding / index layout (pad tuple, shapes, reflect
+indices of yp) is bit-exact; the per-sample mean is the correctly rounded fp64 sum and may differ from
+torch's fp32 reduction by 1 ulp (<= 1.2e-7 relative).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cdl_oracle as O
+import cdlnet_video_b200 as cb
+from util import CASES, load_case, module_from_case, case_inputs
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 2e-5
+TOL_SPEC = 1e-4
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_fixtures_native_fp32(name):
+    d = load_case(name)
+    net = module_from_case(d, name).to(dev())
+    net.precision = "fp32"
+    y, sigma, mask = case_inputs(d, dev())
+    with torch.no_grad():
+        xhat, z = net(y, sigma, mask=mask)
+    assert net._plans, "native path not taken"
+    plan = next(iter(net._plans.values()))
+    assert plan.launch_count() > 0
+    nsp = y.dim() - 2
+    pad = plan.pad[:2 * nsp]
+    assert tuple(pad) == tuple(int(v) for v in d["pad"])                    # bit-exact index layout
+    assert tuple(xhat.shape) == d["xhat"].shape and tuple(z.shape) == d["z"].shape
+    ex = np.abs(xhat.cpu().numpy() - d["xhat"]).max()
+    ez = np.abs(z.cpu().numpy() - d["z"]).max()
+    assert ex <= TOL_FP32 and ez <= TOL_FP32, (ex, ez)
+    # preprocess: yp equals the reference's up to the 1-ulp mean; where mean matches exactly, bit-exact
+    yp, mp, mean = plan.preprocess(y.contiguous(), mask.contiguous() if torch.is_tensor(mask) else None)
+    assert tuple(yp.shape) == d["yp"].shape
+    assert np.abs(mean.cpu().numpy() - d["mean"].reshape(-1)).max() <= 1.2e-7 * max(1.0, np.abs(d["mean"]).max())
+    assert np.abs(yp.cpu().numpy() - d["yp"]).max() <= 2.4e-7
+    if mp is not None:
+        assert np.array_equal(mp.cpu().numpy(), d["mask_p"])                # reflect-pad indices: bit-exact
+
+
+@pytest.mark.parametrize("name", ["cdlnet2d_s2", "gdlnet_s2_c3", "cdlnet2d_nonadaptive"])
+def test_forward_generator_native(name):
+    d = load_case(name)
+    net = module_from_case(d, name).to(dev())
+    net.precision = "fp32"
+    y, sigma, mask = case_inputs(d, dev())
+    with torch.no_grad():
+        items = list(net.forward_generator(y, sigma, mask=mask))
+    assert len(items) == net.K + 1
+    for k in range(net.K):
+        assert np.abs(items[k].cpu().numpy() - d["trace"][k]).max() <= TOL_FP32, k
+    assert np.abs(items[-1].cpu().numpy() - d["xhat"]).max() <= TOL_FP32
+
+
+def _random_case(seed, nsp, N, C, M, K, dims, P, s, sigma_mode, use_mask, neg_t=False):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.rand(N, C, *dims, generator=g)
+    W = torch.randn(M, C, *P, generator=g) * (0.4 / np.sqrt(np.prod(P) * C))
+    A = [W * (1 + 0.1 * torch.randn(W.shape, generator=g)) for _ in range(K)]
+    B = [W * (1 + 0.1 * torch.randn(W.shape, generator=g)) for _ in range(K)]
+    t = torch.rand(K, 2, M, *([1] * nsp), generator=g) * 0.03
+    if neg_t:
+        t[:, 0] -= 0.01
+    if sigma_mode == "none":
+        sigma = None
+    elif sigma_mode == "scalar":
+        sigma = 25.0
+    else:
+        sigma = (10 + 30 * torch.rand(N, generator=g)).reshape(N, *([1] * (nsp + 1)))
+    mask = (torch.rand(N, C, *dims, generator=g) > 0.4).float() if use_mask else 1
+    if use_mask:
+        y = mask * y
+    return y, A, B, t, sigma, mask
+
+
+RANDOM = [
+    # nsp N  C  M    K  dims            P          s  sigma      mask   neg_t
+    (2, 2, 1, 169, 3, (40, 36),       (7, 7),    2, "scalar",  False, False),   # cfg-1 family, M not a multiple of 32
+    (2, 1, 1, 32,  3, (31, 45),       (7, 7),    1, "vector",  False, False),   # cfg-1b family, ragged
+    (2, 2, 3, 64,  3, (30, 34),       (7, 7),    1, "vector",  True,  False),   # cfg-3 (JDD) family
+    (2, 1, 3, 20,  2, (21, 19),       (5, 5),    2, "scalar",  True,  True),    # odd sizes, small filter, negative t
+    (2, 1, 2, 40,  2, (16, 24),       (9, 9),    2, "none",    False, False),
+    (3, 1, 1, 169, 2, (8, 24, 40),    (7, 7, 7), 2, "scalar",  False, False),   # cfg-2 family
+    (3, 2, 1, 24,  3, (7, 13, 15),    (7, 7, 7), 2, "vector",  False, True),    # all-odd extents
+    (3, 1, 1, 16,  2, (6, 12, 20),    (9, 9, 5), 2, "scalar",  False, False),   # args3dmri.json filter
+    (3, 1, 1, 12,  2, (5, 10, 12),    (7, 7, 5), 1, "scalar",  False, False),   # ctor default P, stride 1
+    (3, 1, 2, 8,   2, (4, 9, 11),     (3, 5, 3), 2, "vector",  True,  False),   # mask in 3D, H&W odd
+    (2, 1, 1, 8,   2, (2, 3),         (7, 7),    2, "scalar",  False, False),   # tiny: smaller than the filter
+    (2, 3, 1, 200, 2, (16, 16),       (7, 7),    2, "scalar",  False, False),   # M > 192
+]
+
+
+@pytest.mark.parametrize("idx", range(len(RANDOM)), ids=[f"r{i}" for i in range(len(RANDOM))])
+def test_random_configs_vs_oracle_fp32(idx):
+    cfg = RANDOM[idx]
+    nsp, N, C, M, K, dims, P, s, sigma_mode, use_mask, neg_t = cfg
+    y, A, B, t, sigma, mask = _random_case(100 + idx, nsp, N, C, M, K, dims, P, s, sigma_mode, use_mask, neg_t)
+    xr, zr, ypr, meanr, padr = O.forward_t(y, A, B, t, s, sigma, True, mask)
+    plan = cb.Plan(nsp, N, C, M, K, dims, P, s, has_mask=use_mask, precision="fp32", device=0)
+    assert plan.pad[:2 * nsp] == tuple(padr)
+    d = dev()
+    plan.set_weights([a.to(d) for a in A], [b.to(d) for b in B], t.to(d))
+    c = None
+    if sigma is not None:
+        c = (sigma / 255.0).reshape(-1).to(d) if torch.is_tensor(sigma) else torch.full((N,), sigma / 255.0, device=d)
+        c = c.float().contiguous()
+    xhat, z = plan.denoise(y.to(d).contiguous(), mask.to(d).contiguous() if use_mask else None, c)
+    assert tuple(xhat.shape) == tuple(xr.shape) and tuple(z.shape) == tuple(zr.shape)
+    ex = (xhat.cpu() - xr).abs().max().item()
+    ez = (z.cpu() - zr).abs().max().item()
+    assert ex <= TOL_FP32 and ez <= TOL_FP32, (ex, ez)
+    # support of z: identical up to elements within rounding of the threshold
+    mism = ((z.cpu() != 0) != (zr != 0)).float().mean().item()
+    assert mism <= 1e-3
+
+
+def test_stepwise_api_equals_fused_forward():
+    nsp, N, C, M, K, dims, P, s = 3, 1, 1, 24, 3, (6, 16, 16), (7, 7, 7), 2
+    y, A, B, t, sigma, mask = _random_case(7, nsp, N, C, M, K, dims, P, s, "scalar", False)
+    d = dev()
+    plan = cb.Plan(nsp, N, C, M, K, dims, P, s, precision="fp32")
+    plan.set_weights([a.to(d) for a in A], [b.to(d) for b in B], t.to(d))
+    c = torch.full((N,), 25.0 / 255.0, device=d)
+    yd = y.to(d)
+    xhat, z = plan.denoise(yd, None, c)
+    yp, mp, mean = plan.preprocess(yd)
+    z2 = torch.empty_like(z)
+    r = torch.empty_like(yp)
+    plan.analysis_step(0, yp, z2, c, first=True)
+    for k in range(1, K):
+        plan.synthesis_step(k, z2, r, yp, None, residual=True)
+        plan.analysis_step(k, r, z2, c)
+    plan.synthesis_step(0, z2, r, residual=False)
+    x2 = plan.postprocess(r, mean)
+    assert torch.equal(z, z2) and torch.equal(xhat, x2)       # deterministic kernels: bitwise equal
+
+
+def test_adjoint_and_linearity_properties_at_scale():
+    """Size-independent properties at a config-2-like size: <A x, z> = <x, B z> when the two
+    banks are equal, and with t == 0 the network is linear in y."""
+    nsp, N, C, M, K, dims, P, s = 3, 1, 1, 169, 2, (16, 64, 64), (7, 7, 7), 2
+    g = torch.Generator().manual_seed(3)
+    d = dev()
+    W = (torch.randn(M, C, *P, generator=g) * 0.01).to(d)
+    t0 = torch.zeros(K, 2, M, device=d)
+    plan = cb.Plan(nsp, N, C, M, K, dims, P, s, precision="fp32")
+    plan.set_weights([W] * K, [W] * K, t0)
+    x = torch.randn(plan.fine_shape, generator=g).to(d)
+    zz = torch.randn(plan.z_shape, generator=g).to(d)
+    u = torch.empty(plan.z_shape, device=d)
+    plan.analysis_step(0, x, u, None, first=True)             # t == 0 -> ST is the identity: u = A x
+    bz = torch.empty(plan.fine_shape, device=d)
+    plan.synthesis_step(0, zz, bz, residual=False)
+    lhs = (u.double() * zz.double()).sum().item()
+    rhs = (x.double() * bz.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+    y1 = torch.rand(N, C, *dims, generator=g).to(d)
+    y2 = torch.rand(N, C, *dims, generator=g).to(d)
+    f = lambda y: plan.denoise(y, None, None)[0]
+    lin = f(y1 + 0.5 * y2)
+    assert (lin - (f(y1) + 0.5 * f(y2))).abs().max().item() <= 1e-5
+
+
+def test_errors_are_loud():
+    plan = cb.Plan(2, 1, 1, 8, 2, (16, 16), (7, 7), 2, precision="fp32")
+    y = torch.rand(1, 1, 16, 16, device=dev())
+    with pytest.raises(RuntimeError, match="cdl_set_weights has not been called"):
+        plan.denoise(y, None, None)
+    with pytest.raises(RuntimeError, match="not supported"):
+        cb.Plan(2, 1, 1, 8, 2, (16, 16), (6, 6), 2)
