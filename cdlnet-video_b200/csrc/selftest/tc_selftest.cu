@@ -1,0 +1,134 @@
+// tc_selftest.cu — bring-up checks for the tcgen05 primitives used by the tensor-core kernels.
+// Each case computes D[128*CG x N] = A[128*CG x K] * B[N x K]^T (tf32, fp32 accumulate) with operands
+// that are exactly representable, so any mismatch is a layout / descriptor error, not rounding.
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o tc_selftest tc_selftest.cu
+//   run  : ./tc_selftest <cg:1|2> <ts:0|1> <N> <KS>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../cdl_tc_ptx.cuh"
+
+using namespace cdl::ptx;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+// B packed per K-step j (8 k-values): [j][n/8][k/4][n%8][k%4]  (SBO = 256 B between 8-row groups, LBO = 128 B between k-chunks)
+// For CG == 2 each CTA holds rows [rank*N/2, (rank+1)*N/2) of B, same packing with N/2 rows.
+template <int CG, bool TS>
+__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0;
+  const int KS = K / 8;
+  const int NL = N / CG;                       // B rows held by this CTA
+  float* sB = reinterpret_cast<float*>(smem);                       // KS * NL * 8 floats
+  float* sA = sB + (size_t)KS * NL * 8;                             // KS * 128 * 8 floats (SS only)
+
+  if (warp == 0) { tmem_alloc<CG>(&tmem_base_s, 512); tmem_relinquish<CG>(); }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  // B: this CTA's rows
+  for (int i = tid; i < KS * NL * 8; i += 128) {
+    int j = i / (NL * 8), rem = i % (NL * 8);
+    sB[i] = Bp[(size_t)j * N * 8 + (size_t)rank * NL * 8 + rem];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const int row = rank * 128 + tid;            // global A row of this thread == TMEM lane tid
+  const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+  const int ACOL = 256;                        // A operand columns in TMEM (TS)
+  if (TS) {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t v[8];
+      for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(A[(size_t)row * K + k0 + i]);
+      tmem_st8(lane_addr + ACOL + k0, v);
+    }
+    tmem_wait_st();
+  } else {
+    for (int k = 0; k < K; ++k) {
+      int j = k / 8, kk = k % 8;
+      sA[(size_t)j * 1024 + (tid / 8) * 64 + (kk / 4) * 32 + (tid % 8) * 4 + (kk % 4)] = A[(size_t)row * K + k];
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128 * CG, N);
+    for (int j = 0; j < KS; ++j) {
+      uint64_t bdesc = make_smem_desc_kmajor_noswz(smem_u32(sB) + j * NL * 32, 128, 256);
+      if (TS) mma_tf32_ts<CG>(tbase, tbase + ACOL + j * 8, bdesc, idesc, j > 0);
+      else {
+        uint64_t adesc = make_smem_desc_kmajor_noswz(smem_u32(sA) + j * 4096, 128, 256);
+        mma_tf32_ss<CG>(tbase, adesc, bdesc, idesc, j > 0);
+      }
+    }
+    mma_commit<CG>(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t v[8];
+    tmem_ld8(lane_addr + c0, v);
+    tmem_wait_ld();
+    for (int i = 0; i < 8; ++i) D[(size_t)row * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) tmem_dealloc<CG>(tbase, 512);
+}
+
+int main(int argc, char** argv) {
+  int cg = argc > 1 ? atoi(argv[1]) : 1, ts = argc > 2 ? atoi(argv[2]) : 0, N = argc > 3 ? atoi(argv[3]) : 176, KS = argc > 4 ? atoi(argv[4]) : 7;
+  const int M = 128 * cg, K = KS * 8;
+  std::vector<float> A((size_t)M * K), B((size_t)N * K), Bp((size_t)N * K), D((size_t)M * N, -1.f), R((size_t)M * N);
+  uint32_t s = 12345;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (int)((s >> 20) % 9) - 4; };
+  for (auto& v : A) v = rnd() / 4.0f;
+  for (auto& v : B) v = rnd() / 8.0f;
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      int j = k / 8, kk = k % 8;
+      // full-N packing; a CTA of a pair takes the contiguous row range [rank*N/2, ...) of each K-step block
+      Bp[(size_t)j * N * 8 + (size_t)(n / 8) * 64 + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4)] = B[(size_t)n * K + k];
+    }
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * K + k] * B[(size_t)n * K + k];
+      R[(size_t)m * N + n] = (float)acc;
+    }
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, Bp.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bp.data(), Bp.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice));
+  size_t smem = ((size_t)KS * (N / cg) * 8 + (size_t)KS * 1024) * 4 + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cg); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  void (*fn)(const float*, const float*, float*, int, int) =
+      cg == 1 ? (ts ? k_gemm<1, true> : k_gemm<1, false>) : (ts ? k_gemm<2, true> : k_gemm<2, false>);
+  CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0; long bad = 0;
+  for (size_t i = 0; i < D.size(); ++i) { double e = fabs((double)D[i] - R[i]); if (e > maxerr) maxerr = e; if (e > 1e-5) ++bad; }
+  printf("selftest cg=%d ts=%d M=%d N=%d K=%d : max|err|=%.3e bad=%ld/%zu  %s\n", cg, ts, M, N, K, maxerr, bad, D.size(), bad ? "FAIL" : "PASS");
+  if (bad) {
+    int shown = 0;
+    for (int m = 0; m < M && shown < 6; ++m)
+      for (int n = 0; n < N && shown < 6; ++n)
+        if (fabs(D[(size_t)m * N + n] - R[(size_t)m * N + n]) > 1e-5) { printf("  D[%d][%d]=%g ref=%g\n", m, n, D[(size_t)m * N + n], R[(size_t)m * N + n]); ++shown; }
+  }
+  return bad ? 1 : 0;
+}

@@ -1,0 +1,12 @@
+#!/bin/bash
+# tcgen05 primitive bring-up on the B200 box
+mkdir -p gpurun_out
+T=cdlnet-video_b200/csrc/selftest/tc_selftest
+{
+for cfg in "1 0 176 7" "1 1 176 7" "1 1 64 2" "2 0 176 7" "2 0 192 7" "2 1 192 7" "2 1 176 7" "2 1 256 4" "1 0 256 43"; do
+  echo "== $cfg"; timeout 30 $T $cfg; echo "rc=$?"
+done
+} > gpurun_out/selftest.log 2>&1
+cat gpurun_out/selftest.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python __graft_entry__.py smoke 2>&1 | tail -3

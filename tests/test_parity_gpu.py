@@ -69,12 +69,13 @@ def test_forward_generator_native(name):
 def _random_case(seed, nsp, N, C, M, K, dims, P, s, sigma_mode, use_mask, neg_t=False):
     g = torch.Generator().manual_seed(seed)
     y = torch.rand(N, C, *dims, generator=g)
-    W = torch.randn(M, C, *P, generator=g) * (0.4 / np.sqrt(np.prod(P) * C))
+    # keep the spectral constant of D∘A below 1 (it is ~1.5-2 x M*T*C/s^d for randn banks, reference test.ipynb:171)
+    W = torch.randn(M, C, *P, generator=g) * (0.7 / np.sqrt(2.0 * M * np.prod(P) * C / s ** nsp))
     A = [W * (1 + 0.1 * torch.randn(W.shape, generator=g)) for _ in range(K)]
     B = [W * (1 + 0.1 * torch.randn(W.shape, generator=g)) for _ in range(K)]
-    t = torch.rand(K, 2, M, *([1] * nsp), generator=g) * 0.03
+    t = torch.rand(K, 2, M, *([1] * nsp), generator=g) * 0.01
     if neg_t:
-        t[:, 0] -= 0.01
+        t[:, 0] -= 0.004
     if sigma_mode == "none":
         sigma = None
     elif sigma_mode == "scalar":
