@@ -13,6 +13,7 @@
 #include "cdl_cc.cuh"
 #include "cdl_common.cuh"
 #include "cdl_prepost.cuh"
+#include "cdl_tc_analysis.cuh"
 
 using namespace cdl;
 
@@ -48,6 +49,11 @@ struct cdl_plan {
   float* wB;   // [K][M*C*Pd*Ph*PWP]
   float* t;    // [K][2][M]
   size_t wA_layer, wB_layer;
+  // tcgen05 path (3D, P = 7^3, s = 2, C = 1)
+  bool tc_ana;
+  float* wAtc;         // [K][2 ranks][43][88*8] tf32 filters in UMMA layout
+  size_t wAtc_layer;
+  int sm_count;
   bool have_weights;
   Offsets off;
   uint64_t launches;
@@ -217,7 +223,10 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   g.ndim = d->ndim;
   if (g.Qd > 65535) { delete p; return CDL_ERR_UNSUPPORTED; }
 
-  p->precision_eff = CDL_PREC_FP32;   // tensor-core kernels register themselves below when they cover the geometry
+  p->precision_eff = CDL_PREC_FP32;
+  // tensor-core kernels cover the video network of args3d.json: 3D, 7x7x7, stride 2, one channel, M <= 176
+  const bool tc_geom = nd3 && Pd == 7 && Ph == 7 && Pw == 7 && s == 2 && d->C == 1 && d->M <= tc::kNA && (L.fine[2] % 4) == 0 && !d->has_mask;
+  if (d->precision == CDL_PREC_TF32 && tc_geom) { p->tc_ana = true; p->precision_eff = CDL_PREC_TF32; }
 
   // ---- CUDA-core analysis configuration ----
   const int mb = ceil_div(g.M, 32);
@@ -285,6 +294,17 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     cdl_plan_destroy(p);
     return CDL_CUDA_ERROR_BASE + (int)e;
   }
+  if (p->tc_ana) {
+    p->wAtc_layer = 2 * (size_t)tc::kKSteps * tc::kNAH * 8;
+    int dev_sms = 0;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device);
+    p->sm_count = dev_sms;
+    if ((e = cudaMalloc(&p->wAtc, p->wAtc_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc::k_tc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kAnaSmemBytes)) != cudaSuccess) {
+      cdl_plan_destroy(p);
+      return CDL_CUDA_ERROR_BASE + (int)e;
+    }
+  }
   if ((e = cudaFuncSetAttribute((const void*)p->ana_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ana_smem)) != cudaSuccess ||
       (e = cudaFuncSetAttribute((const void*)p->syn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->syn_smem)) != cudaSuccess) {
     cdl_plan_destroy(p);
@@ -322,6 +342,7 @@ extern "C" void cdl_plan_destroy(cdl_plan_t* p) {
   if (p->wA) cudaFree(p->wA);
   if (p->wB) cudaFree(p->wB);
   if (p->t) cudaFree(p->t);
+  if (p->wAtc) cudaFree(p->wAtc);
   delete p;
 }
 
@@ -367,6 +388,10 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
       long long total = (long long)p->wB_layer;
       int blocks = (int)((total + 255) / 256); if (blocks > 1024) blocks = 1024;
       k_pack_synthesis<<<blocks, 256, 0, st>>>(B[k], p->wB + (size_t)k * p->wB_layer, g.M * g.C * g.Pd * g.Ph, g.Pw, p->PWP);
+      CDL_LAUNCH_CHECK(p);
+    }
+    if (p->tc_ana) {
+      tc::k_pack_tc_analysis<<<64, 256, 0, st>>>(A[k], p->wAtc + (size_t)k * p->wAtc_layer, g.M);
       CDL_LAUNCH_CHECK(p);
     }
   }
@@ -452,6 +477,24 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
   if (!p->have_weights) return CDL_ERR_NO_WEIGHTS;
   if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
   if ((reinterpret_cast<uintptr_t>(z) & 15) || (reinterpret_cast<uintptr_t>(r) & 15)) return CDL_ERR_ALIGN;
+  if (p->tc_ana) {
+    tc::AnaTcParams a;
+    a.g = p->g;
+    a.rin = r; a.z = z;
+    a.wpack = p->wAtc + (size_t)k * p->wAtc_layer;
+    a.t0 = p->t + (size_t)k * 2 * p->g.M;
+    a.t1 = a.t0 + p->g.M;
+    a.cvec = c;
+    a.first = first ? 1 : 0;
+    a.tiles_w = ceil_div(p->g.Qw, tc::kTW);
+    a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
+    a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
+    int pairs = p->sm_count / 2;
+    if (pairs > a.ntiles) pairs = a.ntiles;
+    tc::k_tc_analysis<<<2 * pairs, tc::kThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a);
+    CDL_LAUNCH_CHECK(p);
+    return CDL_OK;
+  }
   AnaParams a;
   a.g = p->g;
   a.rin = r; a.z = z;

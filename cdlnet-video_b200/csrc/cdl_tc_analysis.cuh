@@ -1,0 +1,271 @@
+// cdl_tc_analysis.cuh — tcgen05 analysis step for the video network (3D, P = 7x7x7, s = 2, C = 1):
+//
+//     z <- ST(z - A_k r, t0 + c*t1)            (reference model/net.py:200,205 + :11-14)
+//
+// as an implicit GEMM  U[q, m] = sum_t R[q, t] * W[m, t]  with  M_gemm = 256 coarse sites per CTA pair,
+// N = 176 (169 subbands, zero padded), K = 344 (343 taps + 1 zero column), kind::tf32, fp32 accumulation.
+//
+//   * cta_group::2: the two CTAs of a cluster own 128 coarse sites each (a 1 x 4 x 32 block) and share
+//     the filter bank: each keeps HALF of it (88 subbands x 344 taps = 121 KB) resident in shared memory
+//     for the whole launch, so the filters are read from L2 once per CTA, not once per tile.
+//   * The A operand (im2col of the residual, C = 1) never exists in memory: producer threads (one per
+//     coarse site = one TMEM lane) read their 7x7x7 window from a zero-filled halo tile of r in shared
+//     memory, round to tf32 (RNE — tcgen05 would truncate) and write it straight into TMEM columns with
+//     tcgen05.st; the MMA reads A from TMEM (".ts" form), B from shared memory.
+//   * Accumulators are double buffered in TMEM (2 x 176 columns) so the epilogue of tile i (TMEM ->
+//     registers -> z - u -> soft threshold -> z, one coalesced read + write of z) overlaps the MMAs of
+//     tile i+1; the A operand is a 2-slot ring of 56-column chunks (7 MMAs each).
+//   * Persistent: one CTA pair per SM pair, static round-robin over 256-site tiles.
+//
+// Warp roles (288 threads): warps 0-3 producers, warps 4-7 epilogue, warp 8 MMA issue + TMEM alloc.
+#pragma once
+#include "cdl_common.cuh"
+#include "cdl_tc_ptx.cuh"
+
+namespace cdl {
+namespace tc {
+
+constexpr int kThreads = 288;
+constexpr int kNA = 176;                 // GEMM N of the analysis (subbands, padded)
+constexpr int kNAH = kNA / 2;            // per-CTA half of the filter bank
+constexpr int kP = 7, kTaps = 343;
+constexpr int kKSteps = 43;              // ceil(343 / 8) tf32 MMA K-steps
+constexpr int kChunkRows = 8;            // (td,th) rows per A chunk -> 56 columns = 7 K-steps
+constexpr int kChunks = 7;               // 6 full chunks + 1 chunk of one row (7 taps + 1 zero column)
+constexpr int kTH = 4, kTW = 32;         // coarse tile per CTA: 1 x 4 x 32 (d,h,w); a pair stacks two along h
+constexpr int kRD = 7, kRH = 2 * (kTH - 1) + kP, kRW = 72;   // residual halo tile (fine): 7 x 13 x 72 floats
+constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats
+constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 64;   // TMEM columns: D0 | D1 | A0 | A1  (480 of 512)
+
+struct AnaTcParams {
+  Geo g;
+  const float* rin;     // (N,1,Fd,Fh,Fw) residual (or yp for iteration 0)
+  float* z;             // (N,M,Qd,Qh,Qw) in place
+  const float* wpack;   // this layer: [2 ranks][43 k-steps][11 groups][2][8][4] tf32-rounded filters
+  const float* t0;      // [M]
+  const float* t1;      // [M]
+  const float* cvec;    // [N] or nullptr
+  int first;
+  int tiles_w, tiles_h; // pair tiles along w (32 sites) and h (8 rows)
+  int ntiles;           // N * Qd * tiles_h * tiles_w
+};
+
+constexpr size_t kAnaSmemB = (size_t)kKSteps * kNAH * 8 * sizeof(float);      // 121088
+constexpr size_t kAnaSmemR = 2 * (size_t)kRTile * sizeof(float);              // 52416
+constexpr size_t kAnaSmemT = 2 * kNA * sizeof(float);                         // thresholds t0 | t1
+constexpr size_t kAnaSmemBytes = kAnaSmemB + kAnaSmemR + kAnaSmemT + 256;
+
+// filters (M,1,7,7,7) -> per-rank K-major no-swizzle UMMA layout, tf32 RNE
+__global__ void k_pack_tc_analysis(const float* __restrict__ w, float* __restrict__ out, int M) {
+  const int total = 2 * kKSteps * kNAH * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int e = i % 4, r8 = (i / 4) % 8, kc = (i / 32) % 2, grp = (i / 64) % (kNAH / 8);
+    int ks = (i / (kNAH * 8)) % kKSteps, rank = i / (kNAH * 8 * kKSteps);
+    int m = rank * kNAH + grp * 8 + r8, k = ks * 8 + kc * 4 + e;
+    float v = (m < M && k < kTaps) ? w[(size_t)m * kTaps + k] : 0.0f;
+    out[i] = ptx::to_tf32_rna(v);
+  }
+}
+
+__device__ __forceinline__ void ana_tile_coords(const AnaTcParams& p, int tile, int& n, int& qd, int& qh0, int& qw0) {
+  int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  int th = tile % p.tiles_h; tile /= p.tiles_h;
+  qd = tile % p.g.Qd; n = tile / p.g.Qd;
+  qh0 = th * 2 * kTH; qw0 = tw * kTW;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_analysis(const AnaTcParams p) {
+  using namespace ptx;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  float* sB = reinterpret_cast<float*>(smem_raw);
+  float* sR = reinterpret_cast<float*>(smem_raw + kAnaSmemB);
+  float* sT = reinterpret_cast<float*>(smem_raw + kAnaSmemB + kAnaSmemR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kAnaSmemB + kAnaSmemR + kAnaSmemT);
+  uint64_t* wbar = bars + 0;
+  uint64_t* afull = bars + 1;    // [2]  (used in the leader CTA) producers of both CTAs -> MMA
+  uint64_t* aempty = bars + 3;   // [2]  MMA commit (multicast) -> producers
+  uint64_t* dfull = bars + 5;    // [2]  MMA commit (multicast) -> epilogue
+  uint64_t* dempty = bars + 7;   // [2]  (leader) epilogue warps of both CTAs -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const Geo& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 8) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
+  for (int i = tid; i < kNA; i += kThreads) {
+    sT[i] = (i < g.M) ? p.t0[i] : 0.0f;
+    sT[kNA + i] = (i < g.M) ? p.t1[i] : 0.0f;
+  }
+  __syncthreads();
+  if (tid == 0) {   // this CTA's half of the filter bank: 121088 B in 4 bulk copies
+    mbar_expect_tx(wbar, (uint32_t)kAnaSmemB);
+    const char* src = reinterpret_cast<const char*>(p.wpack) + (size_t)rank * kAnaSmemB;
+    const uint32_t piece = 30272;   // 121088 / 4, multiple of 16
+    for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char*>(sB) + i * piece, src + i * piece, piece, wbar);
+  }
+  mbar_wait(wbar, 0);
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs: barriers initialised, TMEM allocated, filters resident
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp < 4) {
+    // ============================== producers: r tile -> im2col -> TMEM ==============================
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    auto issue_tile_load = [&](int tile, int buf) {
+      int n, qd, qh0, qw0;
+      ana_tile_coords(p, tile, n, qd, qh0, qw0);
+      qh0 += rank * kTH;
+      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;      // tile column 0 <-> fine w = 2*qw0 - 4 (16-B aligned)
+      float* dst = sR + buf * kRTile;
+      const float* src_n = p.rin + (size_t)n * g.fine_vol();
+      for (int row = warp; row < kRD * kRH; row += 4) {
+        const int d = row / kRH, h = row % kRH;
+        const int gd = fd0 + d, gh = fh0 + h;
+        const bool row_ok = gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh;
+        if (lane < kRW / 4) {
+          const int gw = fw0 + 4 * lane;
+          const bool ok = row_ok && gw >= 0 && gw + 4 <= g.Fw;
+          const float* src = ok ? src_n + ((size_t)gd * g.Fh + gh) * g.Fw + gw : p.rin;
+          cp_async16_zfill(dst + row * kRW + 4 * lane, src, ok);
+        }
+      }
+      cp_async_commit();
+    };
+    int it = 0;
+    uint32_t gchunk = 0;
+    if (pair < p.ntiles) issue_tile_load(pair, 0);
+    for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+      const int buf = it & 1;
+      cp_async_wait<0>();
+      named_bar_sync(1, 128);                       // tile `it` landed for everyone; everyone left tile it-1
+      if (tile + npairs < p.ntiles) issue_tile_load(tile + npairs, buf ^ 1);
+      // this thread's coarse site: row `warp` of the CTA tile, column `lane`
+      const float* rs = sR + buf * kRTile + (2 * warp) * kRW + 2 * lane;
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
+        const uint32_t slot = gchunk & 1;
+        mbar_wait(&aempty[slot], ((gchunk >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acol = lane_addr + kColA + slot * kASlot;
+        if (ch < kChunks - 1) {
+          uint32_t v[56];
+#pragma unroll
+          for (int rr = 0; rr < kChunkRows; ++rr) {
+            const int row = ch * kChunkRows + rr, td = row / kP, th = row % kP;
+            const float2* src = reinterpret_cast<const float2*>(rs + (td * kRH + th) * kRW);
+            float2 a = src[0], b = src[1], c = src[2], d = src[3];      // fine w = 2q-4 .. 2q+3 ; taps use 2q-3 .. 2q+3
+            v[rr * 7 + 0] = __float_as_uint(to_tf32_rna(a.y));
+            v[rr * 7 + 1] = __float_as_uint(to_tf32_rna(b.x));
+            v[rr * 7 + 2] = __float_as_uint(to_tf32_rna(b.y));
+            v[rr * 7 + 3] = __float_as_uint(to_tf32_rna(c.x));
+            v[rr * 7 + 4] = __float_as_uint(to_tf32_rna(c.y));
+            v[rr * 7 + 5] = __float_as_uint(to_tf32_rna(d.x));
+            v[rr * 7 + 6] = __float_as_uint(to_tf32_rna(d.y));
+          }
+          tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&v[0]));
+          tmem_st16(acol + 32, *reinterpret_cast<const uint32_t(*)[16]>(&v[32]));
+          tmem_st8(acol + 48, *reinterpret_cast<const uint32_t(*)[8]>(&v[48]));
+        } else {
+          uint32_t v[8];
+          const float2* src = reinterpret_cast<const float2*>(rs + (6 * kRH + 6) * kRW);
+          float2 a = src[0], b = src[1], c = src[2], d = src[3];
+          v[0] = __float_as_uint(to_tf32_rna(a.y)); v[1] = __float_as_uint(to_tf32_rna(b.x));
+          v[2] = __float_as_uint(to_tf32_rna(b.y)); v[3] = __float_as_uint(to_tf32_rna(c.x));
+          v[4] = __float_as_uint(to_tf32_rna(c.y)); v[5] = __float_as_uint(to_tf32_rna(d.x));
+          v[6] = __float_as_uint(to_tf32_rna(d.y)); v[7] = 0u;
+          tmem_st8(acol, v);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&afull[slot], 0);
+      }
+    }
+  } else if (warp < 8) {
+    // ============================== epilogue: TMEM -> z update ==============================
+    const int ew = warp - 4;
+    const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
+    int it = 0;
+    for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+      const uint32_t ds = it & 1;
+      int n, qd, qh0, qw0;
+      ana_tile_coords(p, tile, n, qd, qh0, qw0);
+      const int qh = qh0 + rank * kTH + ew, qw = qw0 + lane;
+      const bool valid = qh < g.Qh && qw < g.Qw;
+      const float cval = p.cvec ? p.cvec[n] : 0.0f;
+      float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw;    // + m * coarse_vol
+      const size_t mstride = (size_t)g.coarse_vol();
+      mbar_wait(&dfull[ds], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mc = 0; mc < kNA / 16; ++mc) {
+        uint32_t u[16];
+        tmem_ld16(lane_addr + kColD + ds * kNA + mc * 16, u);
+        float zin[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int m = mc * 16 + i;
+          zin[i] = (valid && !p.first && m < g.M) ? zq[m * mstride] : 0.0f;
+        }
+        tmem_wait_ld();
+        if (mc == kNA / 16 - 1) {                 // accumulator fully read: hand the TMEM slot back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&dempty[ds], 0);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int m = mc * 16 + i;
+          if (valid && m < g.M) {
+            const float uu = __uint_as_float(u[i]);
+            const float v = p.first ? uu : __fsub_rn(zin[i], uu);
+            zq[m * mstride] = soft_threshold(v, make_tau(sT[m], sT[kNA + m], cval));
+          }
+        }
+      }
+    }
+  } else {
+    // ============================== MMA issue (leader CTA, one thread) ==============================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(256, kNA);
+      const uint32_t sB_addr = smem_u32(sB);
+      int it = 0;
+      uint32_t gchunk = 0;
+      for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+        const uint32_t ds = it & 1;
+        mbar_wait_cluster(&dempty[ds], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tbase + kColD + ds * kNA;
+        for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
+          const uint32_t slot = gchunk & 1;
+          mbar_wait_cluster(&afull[slot], (gchunk >> 1) & 1);
+          tc_fence_after();
+          const int nsteps = (ch < kChunks - 1) ? 7 : 1;
+          for (int j = 0; j < nsteps; ++j) {
+            const int ks = ch * 7 + j;
+            const uint64_t bdesc = make_smem_desc_kmajor_noswz(sB_addr + ks * (kNAH * 32), 128, 256);
+            mma_tf32_ts<2>(dcol, tbase + kColA + slot * kASlot + j * 8, bdesc, idesc, ks > 0);
+          }
+          mma_commit<2>(&aempty[slot]);             // A slot reusable once these MMAs have read it
+        }
+        mma_commit<2>(&dfull[ds]);                  // accumulator complete -> epilogue (both CTAs)
+      }
+    }
+    __syncwarp();                                   // reconverge warp 8 before the aligned cluster barrier
+  }
+  // teardown: everyone done (all MMAs were consumed by the epilogues before they exit)
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 8) tmem_dealloc<2>(tbase, 512);
+}
+
+}  // namespace tc
+}  // namespace cdl

@@ -8,5 +8,5 @@ for cfg in "1 0 176 7" "1 1 176 7" "1 1 64 2" "2 0 176 7" "2 0 192 7" "2 1 192 7
 done
 } > gpurun_out/selftest.log 2>&1
 cat gpurun_out/selftest.log
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python -m pytest tests -m gpu -x -q -s 2>&1 | tail -15
 python __graft_entry__.py smoke 2>&1 | tail -3

@@ -1,0 +1,81 @@
+"""GPU parity of the tcgen05 (tf32) kernel family for the video network (3D, P=7^3, s=2, C=1).
+
+Tolerance per north_star: max-abs <= 1e-4 on xhat, PSNR within 0.01 dB, against the fp32 oracle
+(TF32 disabled: the oracle is torch CPU fp32).  Operands are rounded to tf32 with RNE inside the
+kernels; accumulation is fp32 in TMEM.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cdl_oracle as O
+import cdlnet_video_b200 as cb
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _weights(M, K, seed, scale):
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn(M, 1, 7, 7, 7, generator=g) * scale
+    A = [W * (1 + 0.03 * torch.randn(W.shape, generator=g)) for _ in range(K)]
+    B = [W * (1 + 0.03 * torch.randn(W.shape, generator=g)) for _ in range(K)]
+    return A, B, g
+
+
+def _run(plan, A, B, t, y, c):
+    d = torch.device("cuda", 0)
+    plan.set_weights([a.to(d) for a in A], [b.to(d) for b in B], t.to(d))
+    return plan.denoise(y.to(d).contiguous(), None, c.to(d) if c is not None else None)
+
+
+@pytest.mark.parametrize("dims,N,M,K", [((8, 32, 64), 1, 169, 3), ((6, 20, 40), 2, 169, 2), ((4, 16, 36), 1, 64, 4),
+                                         ((16, 64, 64), 1, 169, 6), ((7, 13, 44), 1, 100, 3)])
+def test_tf32_small_vs_oracle(dims, N, M, K):
+    A, B, g = _weights(M, K, 11, 0.7 / np.sqrt(2.0 * M * 343 / 8))
+    t = torch.rand(K, 2, M, 1, 1, 1, generator=g) * 0.01
+    y = torch.rand(N, 1, *dims, generator=g)
+    sigma = torch.tensor([25.0, 15.0][:N]).reshape(N, 1, 1, 1, 1)
+    xr, zr, *_ = O.forward_t(y, A, B, t, 2, sigma, True, 1)
+    plan = cb.Plan(3, N, 1, M, K, dims, (7, 7, 7), 2, precision="tf32")
+    if plan.fine[2] % 4 == 0:
+        assert plan.precision == "tf32", "tensor-core path not selected"
+    xhat, z = _run(plan, A, B, t, y, (sigma / 255.0).reshape(-1).float())
+    ex = (xhat.cpu() - xr).abs().max().item()
+    ez = (z.cpu() - zr).abs().max().item()
+    assert ex <= TOL and ez <= TOL, (ex, ez)
+    # same plan geometry on the exact fp32 family agrees too (cross-check of the two kernel families)
+    plan32 = cb.Plan(3, N, 1, M, K, dims, (7, 7, 7), 2, precision="fp32")
+    x32, z32 = _run(plan32, A, B, t, y, (sigma / 255.0).reshape(-1).float())
+    assert (x32 - xhat).abs().max().item() <= TOL
+
+
+def test_tf32_cfg2_full_size_parity():
+    """BASELINE config 2 at full size: CDLNetVideo(K=30, M=169, P=7^3, s=2) on one 16x256x256 clip, sigma=25,
+    synthetic weights per SURVEY 8(d).  max|xhat - oracle| <= 1e-4 and |PSNR - PSNR_oracle| <= 0.01 dB."""
+    import bench
+    d = torch.device("cuda", 0)
+    K, M = bench.CFG["K"], bench.CFG["M"]
+    A, B, u = bench.synthetic_weights(torch, d)
+    clean, y = bench.synthetic_clip(torch, 1, seed=0, device=d)
+    plan = cb.Plan(3, 1, 1, M, K, bench.CLIP, (7, 7, 7), 2, precision="tf32")
+    assert plan.precision == "tf32"
+    plan.set_weights(A, B, torch.zeros(K, 2, M, device=d))
+    yp, _, _ = plan.preprocess(y)
+    z0 = torch.empty(plan.z_shape, device=d)
+    plan.analysis_step(0, yp, z0, None, first=True)
+    q = torch.quantile(z0[0].abs().reshape(M, -1)[:, ::8].float(), 0.85, dim=1)
+    t = bench.thresholds_from_quantile(torch, q, u)
+    plan.set_weights(A, B, t)
+    c = torch.full((1,), bench.SIGMA / 255.0, device=d)
+    xhat, z = plan.denoise(y, None, c)
+    xr, zr, *_ = O.forward_t(y.cpu(), [a.cpu() for a in A], [b.cpu() for b in B], t.cpu().reshape(K, 2, M, 1, 1, 1),
+                             2, bench.SIGMA, True, 1)
+    ex = (xhat.cpu() - xr).abs().max().item()
+    p1, p0 = O.psnr(xhat.cpu().numpy(), clean.cpu().numpy()), O.psnr(xr.numpy(), clean.cpu().numpy())
+    nnz = (zr != 0).float().mean().item()
+    mism = ((z.cpu() != 0) != (zr != 0)).float().mean().item()
+    print(f"cfg2 full: max|dxhat|={ex:.3e} psnr {p1:.4f} vs {p0:.4f} nnz={nnz:.3f} support mismatch={mism:.2e}")
+    assert ex <= TOL, ex
+    assert abs(p1 - p0) <= 0.01
+    assert 0.01 < nnz < 0.5
