@@ -14,6 +14,7 @@
 #include "cdl_common.cuh"
 #include "cdl_prepost.cuh"
 #include "cdl_tc_analysis.cuh"
+#include "cdl_tc_synthesis.cuh"
 
 using namespace cdl;
 
@@ -50,9 +51,10 @@ struct cdl_plan {
   float* t;    // [K][2][M]
   size_t wA_layer, wB_layer;
   // tcgen05 path (3D, P = 7^3, s = 2, C = 1)
-  bool tc_ana;
+  bool tc_ana, tc_syn;
   float* wAtc;         // [K][2 ranks][43][88*8] tf32 filters in UMMA layout
-  size_t wAtc_layer;
+  float* wBtc;         // [K][2 ranks][176*176]
+  size_t wAtc_layer, wBtc_layer;
   int sm_count;
   bool have_weights;
   Offsets off;
@@ -226,7 +228,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   p->precision_eff = CDL_PREC_FP32;
   // tensor-core kernels cover the video network of args3d.json: 3D, 7x7x7, stride 2, one channel, M <= 176
   const bool tc_geom = nd3 && Pd == 7 && Ph == 7 && Pw == 7 && s == 2 && d->C == 1 && d->M <= tc::kNA && (L.fine[2] % 4) == 0 && !d->has_mask;
-  if (d->precision == CDL_PREC_TF32 && tc_geom) { p->tc_ana = true; p->precision_eff = CDL_PREC_TF32; }
+  if (d->precision == CDL_PREC_TF32 && tc_geom) { p->tc_ana = true; p->tc_syn = (getenv("CDL_TC_SYN") ? atoi(getenv("CDL_TC_SYN")) != 0 : true); p->precision_eff = CDL_PREC_TF32; }
 
   // ---- CUDA-core analysis configuration ----
   const int mb = ceil_div(g.M, 32);
@@ -299,7 +301,10 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     int dev_sms = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device);
     p->sm_count = dev_sms;
+    p->wBtc_layer = 2 * (size_t)tc::kKB * tc::kKB;
     if ((e = cudaMalloc(&p->wAtc, p->wAtc_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&p->wBtc, p->wBtc_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kAnaSmemBytes)) != cudaSuccess) {
       cdl_plan_destroy(p);
       return CDL_CUDA_ERROR_BASE + (int)e;
@@ -343,6 +348,7 @@ extern "C" void cdl_plan_destroy(cdl_plan_t* p) {
   if (p->wB) cudaFree(p->wB);
   if (p->t) cudaFree(p->t);
   if (p->wAtc) cudaFree(p->wAtc);
+  if (p->wBtc) cudaFree(p->wBtc);
   delete p;
 }
 
@@ -392,6 +398,8 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
     }
     if (p->tc_ana) {
       tc::k_pack_tc_analysis<<<64, 256, 0, st>>>(A[k], p->wAtc + (size_t)k * p->wAtc_layer, g.M);
+      CDL_LAUNCH_CHECK(p);
+      tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M);
       CDL_LAUNCH_CHECK(p);
     }
   }
@@ -519,6 +527,30 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
   if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
   if ((reinterpret_cast<uintptr_t>(z) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (yp && (reinterpret_cast<uintptr_t>(yp) & 15)) || (mask_p && (reinterpret_cast<uintptr_t>(mask_p) & 15))) return CDL_ERR_ALIGN;
+  if (p->tc_syn) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const long long nfine = (long long)p->g.N * p->g.fine_vol();
+    if (residual) {
+      long long n4 = nfine / 4, blocks = (n4 + 255) / 256;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      tc::k_neg_copy<<<(int)blocks, 256, 0, st>>>(yp, out, n4);        // out <- -yp ; the scatter-add completes B z - yp
+      CDL_LAUNCH_CHECK(p);
+    } else {
+      CDL_CUDA(cudaMemsetAsync(out, 0, (size_t)nfine * sizeof(float), st));
+    }
+    tc::SynTcParams a;
+    a.g = p->g;
+    a.z = z; a.out = out;
+    a.wpack = p->wBtc + (size_t)k * p->wBtc_layer;
+    a.tiles_w = ceil_div(p->g.Qw, tc::kTW);
+    a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
+    a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
+    int pairs = p->sm_count / 2;
+    if (pairs > a.ntiles) pairs = a.ntiles;
+    tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
+    CDL_LAUNCH_CHECK(p);
+    return CDL_OK;
+  }
   SynParams s = p->syn_cfg;
   s.z = z;
   s.wB = p->wB + (size_t)k * p->wB_layer;
