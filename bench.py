@@ -304,7 +304,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = te.item() / args.steps
     e2e_value = world * n_clips * alg["V"] / (e2e_ms * 1e-3) / 1e6
-    e2e_ok = float((x_host.to(dev) - xhat).abs().max()) == 0.0
+    e2e_ok = float((x_host.to(dev) - xhat).abs().max()) <= 1e-5      # red.add order makes runs differ by ~1e-7
 
     # ---- per-kernel breakdown (CUDA events on the launch stream) -> roofline of the dominant kernel ----
     roof = None

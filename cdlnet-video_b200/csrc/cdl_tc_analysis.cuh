@@ -17,7 +17,8 @@
 //     tile i+1; the A operand is a 2-slot ring of 56-column chunks (7 MMAs each).
 //   * Persistent: one CTA pair per SM pair, static round-robin over 256-site tiles.
 //
-// Warp roles (288 threads): warps 0-3 producers, warps 4-7 epilogue, warp 8 MMA issue + TMEM alloc.
+// Warp roles (416 threads): warps 0-3 producers, warps 4-11 epilogue (two per TMEM lane quadrant, each owning
+// half of the subbands and prefetching its z values into registers while the MMAs run), warp 12 MMA issue + TMEM alloc.
 #pragma once
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
@@ -25,7 +26,8 @@
 namespace cdl {
 namespace tc {
 
-constexpr int kThreads = 288;
+constexpr int kThreads = 416;
+constexpr int kMmaWarp = 12;
 constexpr int kNA = 176;                 // GEMM N of the analysis (subbands, padded)
 constexpr int kNAH = kNA / 2;            // per-CTA half of the filter bank
 constexpr int kP = 7, kTaps = 343;
@@ -95,10 +97,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
 
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 16); }
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
+  if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
   for (int i = tid; i < kNA; i += kThreads) {
     sT[i] = (i < g.M) ? p.t0[i] : 0.0f;
     sT[kNA + i] = (i < g.M) ? p.t1[i] : 0.0f;
@@ -189,45 +191,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         if (lane == 0) mbar_arrive_cluster(&afull[slot], 0);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kMmaWarp) {
     // ============================== epilogue: TMEM -> z update ==============================
-    const int ew = warp - 4;
-    const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
+    // warp = 4 + 4*half + quad: TMEM lanes [32*quad, 32*quad+32) (tile row `quad`), subbands [88*half, 88*half+88)
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int m0 = half * kNAH;
+    const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
+    const size_t mstride = (size_t)g.coarse_vol();
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       const uint32_t ds = it & 1;
       int n, qd, qh0, qw0;
       ana_tile_coords(p, tile, n, qd, qh0, qw0);
-      const int qh = qh0 + rank * kTH + ew, qw = qw0 + lane;
+      const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
       const bool valid = qh < g.Qh && qw < g.Qw;
       const float cval = p.cvec ? p.cvec[n] : 0.0f;
-      float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw;    // + m * coarse_vol
-      const size_t mstride = (size_t)g.coarse_vol();
+      float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
+      // all of this thread's z values are requested BEFORE waiting for the accumulator: the DRAM latency
+      // hides behind the MMAs of this tile (88 loads in flight per thread, coalesced 128 B per warp and subband)
+      float zin[kNAH];
+#pragma unroll
+      for (int i = 0; i < kNAH; ++i) zin[i] = (valid && !p.first && m0 + i < g.M) ? __ldg(zq + i * mstride) : 0.0f;
       mbar_wait(&dfull[ds], (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int mc = 0; mc < kNA / 16; ++mc) {
-        uint32_t u[16];
-        tmem_ld16(lane_addr + kColD + ds * kNA + mc * 16, u);
-        float zin[16];
+      const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int m = mc * 16 + i;
-          zin[i] = (valid && !p.first && m < g.M) ? zq[m * mstride] : 0.0f;
-        }
+      for (int b = 0; b < 6; ++b) {
+        uint32_t u[16];
+        if (b < 5) tmem_ld16(dcol + b * 16, u);
+        else tmem_ld8(dcol + 80, *reinterpret_cast<uint32_t(*)[8]>(&u[0]));
         tmem_wait_ld();
-        if (mc == kNA / 16 - 1) {                 // accumulator fully read: hand the TMEM slot back to the MMA warp
+        if (b == 5) {                              // accumulator fully read: hand the TMEM slot back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&dempty[ds], 0);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int m = mc * 16 + i;
+        for (int i = 0; i < (b < 5 ? 16 : 8); ++i) {
+          const int mi = b * 16 + i, m = m0 + mi;
           if (valid && m < g.M) {
             const float uu = __uint_as_float(u[i]);
-            const float v = p.first ? uu : __fsub_rn(zin[i], uu);
-            zq[m * mstride] = soft_threshold(v, make_tau(sT[m], sT[kNA + m], cval));
+            const float v = p.first ? uu : __fsub_rn(zin[mi], uu);
+            zq[mi * mstride] = soft_threshold(v, make_tau(sT[m], sT[kNA + m], cval));
           }
         }
       }
@@ -259,12 +264,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         mma_commit<2>(&dfull[ds]);                  // accumulator complete -> epilogue (both CTAs)
       }
     }
-    __syncwarp();                                   // reconverge warp 8 before the aligned cluster barrier
+    __syncwarp();                                   // reconverge the MMA warp before the aligned cluster barrier
   }
   // teardown: everyone done (all MMAs were consumed by the epilogues before they exit)
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 8) tmem_dealloc<2>(tbase, 512);
+  if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
 }
 
 }  // namespace tc

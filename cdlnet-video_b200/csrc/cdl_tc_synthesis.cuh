@@ -163,10 +163,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
 
   if (tid == 0) {
     mbar_init(wbar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
     fence_mbar_init();
   }
-  if (warp == 8) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
+  if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
   for (int i = tid; i < kXTile; i += kThreads) sX[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
@@ -182,63 +182,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   const uint32_t tbase = *tmem_slot;
   const size_t mstride = (size_t)g.coarse_vol();
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ============================== producers: z[m, q] -> tf32 -> TMEM A ==============================
-    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    // warp = 4*half + quad: TMEM lanes of tile row `quad`, subbands [88*half, 88*half+88)
+    const int quad = warp & 3, half = warp >> 2;
+    const int m0 = half * (kKB / 2);
+    const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       const uint32_t ab = it & 1;
       int n, qd, qh0, qw0;
       syn_tile_coords(p, tile, n, qd, qh0, qw0);
-      const int qh = qh0 + rank * kTH + warp, qw = qw0 + lane;
+      const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
       const bool valid = qh < g.Qh && qw < g.Qw;
-      const float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw;
-      // pull the next tile's rows of z towards L2 while this one is converted
-      if (tile + npairs < p.ntiles) {
-        int n2, qd2, qh02, qw02;
-        syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + warp;
-        if (qh2 < g.Qh) {
-          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02;
-          for (int m = lane; m < g.M; m += 32) prefetch_l2(z2 + m * mstride);
-        }
-      }
+      const float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
+      // request all 88 values before waiting for the TMEM buffer: the loads overlap the MMAs still reading it
+      uint32_t v[kKB / 2];
+#pragma unroll
+      for (int i = 0; i < kKB / 2; ++i) v[i] = __float_as_uint((valid && m0 + i < g.M) ? __ldg(zq + i * mstride) : 0.0f);
       mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t acol = lane_addr + kColA0 + ab * kKB;
-#pragma unroll 1
-      for (int mb = 0; mb < 5; ++mb) {
-        uint32_t v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = mb * 32 + i;
-          float x = (valid && m < g.M) ? __ldg(zq + m * mstride) : 0.0f;
-          v[i] = __float_as_uint(x);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
-        tmem_st32(acol + mb * 32, v);
-      }
-      {
-        uint32_t v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int m = 160 + i;
-          float x = (valid && m < g.M) ? __ldg(zq + m * mstride) : 0.0f;
-          v[i] = __float_as_uint(to_tf32_rna(x));
-        }
-        tmem_st16(acol + 160, v);
-      }
+      for (int i = 0; i < kKB / 2; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
+      const uint32_t acol = lane_addr + kColA0 + ab * kKB + m0;
+      tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&v[0]));
+      tmem_st32(acol + 32, *reinterpret_cast<const uint32_t(*)[32]>(&v[32]));
+      tmem_st16(acol + 64, *reinterpret_cast<const uint32_t(*)[16]>(&v[64]));
+      tmem_st8(acol + 80, *reinterpret_cast<const uint32_t(*)[8]>(&v[80]));
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&afull[ab], 0);
     }
-  } else if (warp < 8) {
+  } else if (warp < kMmaWarp) {
     // ============================== epilogue: col2im ==============================
-    const int ew = warp - 4;
+    const int ew = warp - 8;
     const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
-    const int et = tid - 128;
+    const int et = tid - 256;
     uint32_t gch = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs) {
       float rowv[7];
@@ -304,7 +284,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   }
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 8) tmem_dealloc<2>(tbase, 512);
+  if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
 }
 
 }  // namespace tc
