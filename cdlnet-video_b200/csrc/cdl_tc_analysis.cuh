@@ -88,7 +88,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
   uint64_t* aempty = bars + 3;   // [2]  MMA commit (multicast) -> producers
   uint64_t* dfull = bars + 5;    // [2]  MMA commit (multicast) -> epilogue
   uint64_t* dempty = bars + 7;   // [2]  (leader) epilogue warps of both CTAs -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* wready = bars + 9;   //      (leader) the peer CTA's filters have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,6 +98,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
 
   if (tid == 0) {
     mbar_init(wbar, 1);
+    mbar_init(wready, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 16); }
     fence_mbar_init();
   }
@@ -112,9 +114,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
     const uint32_t piece = 30272;   // 121088 / 4, multiple of 16
     for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char*>(sB) + i * piece, src + i * piece, piece, wbar);
   }
-  mbar_wait(wbar, 0);
   tc_fence_before();
-  cluster_sync_all();          // both CTAs: barriers initialised, TMEM allocated, filters resident
+  cluster_sync_all();          // both CTAs: barriers initialised, TMEM allocated (filters may still be in flight)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
 
@@ -207,11 +208,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
       const bool valid = qh < g.Qh && qw < g.Qw;
       const float cval = p.cvec ? p.cvec[n] : 0.0f;
       float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
-      // all of this thread's z values are requested BEFORE waiting for the accumulator: the DRAM latency
-      // hides behind the MMAs of this tile (88 loads in flight per thread, coalesced 128 B per warp and subband)
-      float zin[kNAH];
+      // pull the next tile's z rows towards L2 (676 lines of 128 B per CTA tile, spread over the 256 epilogue threads)
+      if (!p.first && tile + npairs < p.ntiles) {
+        int n2, qd2, qh02, qw02;
+        ana_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
+        const int qh2 = qh02 + rank * kTH + quad;
+        if (qh2 < g.Qh) {
+          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02;
+          for (int m = m0 + lane; m < m0 + kNAH && m < g.M; m += 32) prefetch_l2(z2 + m * mstride);
+        }
+      }
+      auto load_z = [&](float (&dst)[16], int b) {
 #pragma unroll
-      for (int i = 0; i < kNAH; ++i) zin[i] = (valid && !p.first && m0 + i < g.M) ? __ldg(zq + i * mstride) : 0.0f;
+        for (int i = 0; i < 16; ++i) {
+          const int mi = b * 16 + i;
+          dst[i] = (valid && !p.first && mi < kNAH && m0 + mi < g.M) ? __ldg(zq + mi * mstride) : 0.0f;
+        }
+      };
+      float zcur[16], znext[16];
+      load_z(zcur, 0);                              // first batch of z is requested before the accumulator is ready
       mbar_wait(&dfull[ds], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
@@ -220,6 +235,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         uint32_t u[16];
         if (b < 5) tmem_ld16(dcol + b * 16, u);
         else tmem_ld8(dcol + 80, *reinterpret_cast<uint32_t(*)[8]>(&u[0]));
+        if (b < 5) load_z(znext, b + 1);
         tmem_wait_ld();
         if (b == 5) {                              // accumulator fully read: hand the TMEM slot back to the MMA warp
           tc_fence_before();
@@ -231,15 +247,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
           const int mi = b * 16 + i, m = m0 + mi;
           if (valid && m < g.M) {
             const float uu = __uint_as_float(u[i]);
-            const float v = p.first ? uu : __fsub_rn(zin[mi], uu);
+            const float v = p.first ? uu : __fsub_rn(zcur[i], uu);
             zq[mi * mstride] = soft_threshold(v, make_tau(sT[m], sT[kNA + m], cval));
           }
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) zcur[i] = znext[i];
       }
     }
   } else {
     // ============================== MMA issue (leader CTA, one thread) ==============================
+    if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0 && lane == 0) {
+      mbar_wait(wbar, 0);
+      mbar_wait_cluster(wready, 0);
       const uint32_t idesc = make_idesc_tf32(256, kNA);
       const uint32_t sB_addr = smem_u32(sB);
       int it = 0;

@@ -154,7 +154,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   uint64_t* aempty = bars + 3;   // [2] MMA commit (multicast) -> producers
   uint64_t* dfull = bars + 5;    // [2] MMA commit (multicast) -> epilogue
   uint64_t* dempty = bars + 7;   // [2] (leader) epilogue warps of both CTAs -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* wready = bars + 9;   //     (leader) the peer CTA's filters have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -163,6 +164,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
 
   if (tid == 0) {
     mbar_init(wbar, 1);
+    mbar_init(wready, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
     fence_mbar_init();
   }
@@ -175,9 +177,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     const uint32_t piece = 30976;   // 123904 / 4
     for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char*>(sB) + i * piece, src + i * piece, piece, wbar);
   }
-  mbar_wait(wbar, 0);
   tc_fence_before();
-  cluster_sync_all();
+  cluster_sync_all();          // barriers initialised, TMEM allocated (filters may still be in flight)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
   const size_t mstride = (size_t)g.coarse_vol();
@@ -196,19 +197,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
       const bool valid = qh < g.Qh && qw < g.Qw;
       const float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
-      // request all 88 values before waiting for the TMEM buffer: the loads overlap the MMAs still reading it
-      uint32_t v[kKB / 2];
+      // pull the next tile's rows of z towards L2 while this one is converted
+      if (tile + npairs < p.ntiles) {
+        int n2, qd2, qh02, qw02;
+        syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
+        const int qh2 = qh02 + rank * kTH + quad;
+        if (qh2 < g.Qh) {
+          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02;
+          for (int m = m0 + lane; m < m0 + kKB / 2 && m < g.M; m += 32) prefetch_l2(z2 + m * mstride);
+        }
+      }
+      const uint32_t acol = lane_addr + kColA0 + ab * kKB + m0;
+      uint32_t v[32];
 #pragma unroll
-      for (int i = 0; i < kKB / 2; ++i) v[i] = __float_as_uint((valid && m0 + i < g.M) ? __ldg(zq + i * mstride) : 0.0f);
-      mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1);
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((valid && m0 + i < g.M) ? __ldg(zq + i * mstride) : 0.0f);
+      mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1);     // first batch is in flight while the MMAs still read this buffer
       tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < kKB / 2; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
-      const uint32_t acol = lane_addr + kColA0 + ab * kKB + m0;
-      tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&v[0]));
-      tmem_st32(acol + 32, *reinterpret_cast<const uint32_t(*)[32]>(&v[32]));
-      tmem_st16(acol + 64, *reinterpret_cast<const uint32_t(*)[16]>(&v[64]));
-      tmem_st8(acol + 80, *reinterpret_cast<const uint32_t(*)[8]>(&v[80]));
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
+      tmem_st32(acol, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((valid && m0 + 32 + i < g.M) ? __ldg(zq + (32 + i) * mstride) : 0.0f);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
+      tmem_st32(acol + 32, v);
+      {
+        uint32_t w[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) w[i] = __float_as_uint((valid && m0 + 64 + i < g.M) ? __ldg(zq + (64 + i) * mstride) : 0.0f);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) w[i] = __float_as_uint(to_tf32_rna(__uint_as_float(w[i])));
+        tmem_st16(acol + 64, *reinterpret_cast<const uint32_t(*)[16]>(&w[0]));
+        tmem_st8(acol + 80, *reinterpret_cast<const uint32_t(*)[8]>(&w[16]));
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -255,7 +276,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     }
   } else {
     // ============================== MMA issue (leader CTA, one thread) ==============================
+    if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0 && lane == 0) {
+      mbar_wait(wbar, 0);
+      mbar_wait_cluster(wready, 0);
       const uint32_t sB_addr = smem_u32(sB);
       int it = 0;
       uint32_t gch = 0;
