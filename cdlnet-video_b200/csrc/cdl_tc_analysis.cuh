@@ -199,14 +199,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
     const int m0 = half * kNAH;
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     const size_t mstride = (size_t)g.coarse_vol();
+    const int mcount = min(kNAH, max(0, g.M - m0));             // real subbands in this warp's half
+    const uint32_t usign = p.first ? 0x80000000u : 0u;          // iteration 0: z_in = 0 and v = +u  (0 - (-u))
+    float* sTau = sT;                                           // tau[m] of the sample the current tile belongs to
+    int n_tau = -1;
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       const uint32_t ds = it & 1;
       int n, qd, qh0, qw0;
       ana_tile_coords(p, tile, n, qd, qh0, qw0);
+      if (n != n_tau) {                                         // uniform over the 8 epilogue warps (same tile sequence)
+        named_bar_sync(3, 256);
+        const float cval = p.cvec ? p.cvec[n] : 0.0f;
+        for (int i = tid - 128; i < kNA; i += 256) sTau[i] = (i < g.M) ? make_tau(p.t0[i], p.t1[i], cval) : 0.0f;
+        named_bar_sync(3, 256);
+        n_tau = n;
+      }
       const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
       const bool valid = qh < g.Qh && qw < g.Qw;
-      const float cval = p.cvec ? p.cvec[n] : 0.0f;
+      const int cnt = valid ? mcount : 0;                       // subbands this thread reads / writes
+      const int cnt_ld = p.first ? 0 : cnt;
       float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
       // pull the next tile's z rows towards L2 (676 lines of 128 B per CTA tile, spread over the 256 epilogue threads)
       if (!p.first && tile + npairs < p.ntiles) {
@@ -214,45 +226,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         ana_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
         const int qh2 = qh02 + rank * kTH + quad;
         if (qh2 < g.Qh) {
-          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02;
-          for (int m = m0 + lane; m < m0 + kNAH && m < g.M; m += 32) prefetch_l2(z2 + m * mstride);
+          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02 + (size_t)m0 * mstride;
+          for (int m = lane; m < mcount; m += 32) prefetch_l2(z2 + m * mstride);
         }
       }
-      auto load_z = [&](float (&dst)[16], int b) {
+      float zc[16];
+      {
+        const float* pz = zq;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int mi = b * 16 + i;
-          dst[i] = (valid && !p.first && mi < kNAH && m0 + mi < g.M) ? __ldg(zq + mi * mstride) : 0.0f;
-        }
-      };
-      float zcur[16], znext[16];
-      load_z(zcur, 0);                              // first batch of z is requested before the accumulator is ready
+        for (int i = 0; i < 16; ++i) zc[i] = (i < cnt_ld) ? __ldg(pz + i * mstride) : 0.0f;   // batch 0, before the accumulator is ready
+      }
       mbar_wait(&dfull[ds], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
-#pragma unroll
-      for (int b = 0; b < 6; ++b) {
+#pragma unroll 1
+      for (int b = 0; b < 5; ++b) {
         uint32_t u[16];
-        if (b < 5) tmem_ld16(dcol + b * 16, u);
-        else tmem_ld8(dcol + 80, *reinterpret_cast<uint32_t(*)[8]>(&u[0]));
-        if (b < 5) load_z(znext, b + 1);
-        tmem_wait_ld();
-        if (b == 5) {                              // accumulator fully read: hand the TMEM slot back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&dempty[ds], 0);
-        }
+        tmem_ld16(dcol + b * 16, u);
+        float zn[16];
+        {
+          const float* pz = zq + (size_t)(b + 1) * 16 * mstride;
+          const int c2 = cnt_ld - (b + 1) * 16;
 #pragma unroll
-        for (int i = 0; i < (b < 5 ? 16 : 8); ++i) {
-          const int mi = b * 16 + i, m = m0 + mi;
-          if (valid && m < g.M) {
-            const float uu = __uint_as_float(u[i]);
-            const float v = p.first ? uu : __fsub_rn(zcur[i], uu);
-            zq[mi * mstride] = soft_threshold(v, make_tau(sT[m], sT[kNA + m], cval));
+          for (int i = 0; i < 16; ++i) zn[i] = (i < c2) ? __ldg(pz + i * mstride) : 0.0f;     // next batch in flight
+        }
+        tmem_wait_ld();
+        float* po = zq + (size_t)b * 16 * mstride;
+        const int c1 = cnt - b * 16;
+        const float4* tq = reinterpret_cast<const float4*>(sTau + m0 + b * 16);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 t4 = tq[i4];
+          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = i4 * 4 + j;
+            const float v = __fsub_rn(zc[i], __uint_as_float(u[i] ^ usign));
+            if (i < c1) po[i * mstride] = soft_threshold(v, tt[j]);
           }
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) zcur[i] = znext[i];
+        for (int i = 0; i < 16; ++i) zc[i] = zn[i];
+      }
+      {   // tail: columns 80..87
+        uint32_t u[8];
+        tmem_ld8(dcol + 80, u);
+        tmem_wait_ld();
+        tc_fence_before();                         // accumulator fully read: hand the TMEM slot back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&dempty[ds], 0);
+        float* po = zq + (size_t)80 * mstride;
+        const int c1 = cnt - 80;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = __fsub_rn(zc[i], __uint_as_float(u[i] ^ usign));
+          if (i < c1) po[i * mstride] = soft_threshold(v, sTau[m0 + 80 + i]);
+        }
       }
     }
   } else {

@@ -43,6 +43,8 @@ struct SynTcParams {
 };
 
 __host__ __device__ constexpr int syn_chunk_rows(int nc) { return nc < 5 ? 32 : 16; }          // B rows per CTA in chunk nc
+constexpr int kRowsPerChunk = 9;                                                                // (th,td) rows of 7 taps per accumulator chunk
+__host__ __device__ constexpr int syn_chunk_nrows(int nc) { return nc < 5 ? 9 : 4; }
 __host__ __device__ constexpr int syn_chunk_off(int nc) { return nc * (kKBSteps * 32 * 8); }   // float offset of chunk nc
 constexpr size_t kSynSmemB = (size_t)(5 * 32 + 16) * kKB * sizeof(float);                      // 123904
 constexpr size_t kSynSmemX = (size_t)kXTile * sizeof(float);                                   // 26208
@@ -61,11 +63,12 @@ __global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restri
     const int ks = rem / (rows * 8);
     rem %= rows * 8;
     const int grp = rem / 64, kc = (rem / 32) % 2, r8 = (rem / 4) % 8, e = rem % 4;
-    const int n = nc * 64 + rank * rows + grp * 8 + r8;        // GEMM N index = tap in (th,td,tw) order
+    const int j = rank * rows + grp * 8 + r8;                  // column inside accumulator chunk nc
     const int m = ks * 8 + kc * 4 + e;
+    const int row = nc * kRowsPerChunk + j / 7, tw = j % 7;    // (th,td) row index, th-major
     float v = 0.0f;
-    if (n < kTaps && m < M) {
-      const int th = n / 49, td = (n / 7) % 7, tw = n % 7;
+    if (j < 7 * syn_chunk_nrows(nc) && row < 49 && m < M) {
+      const int th = row / 7, td = row % 7;
       v = w[(size_t)m * kTaps + (td * 7 + th) * 7 + tw];
     }
     out[i] = ptx::to_tf32_rna(v);
@@ -80,55 +83,78 @@ __global__ void __launch_bounds__(256) k_neg_copy(const float* __restrict__ yp, 
   }
 }
 
-template <int R>
-struct RowOps {
-  // one (th,td) row of 7 tw-values -> this CTA's fine tile in shared memory
-  static __device__ __forceinline__ void apply(const float (&v)[7], float* xs, int hrow, int lane) {
-    constexpr int th = R / 7, td = R % 7;
-    const unsigned full = 0xffffffffu;
-    float a1 = __shfl_down_sync(full, v[1], 1), a2 = __shfl_down_sync(full, v[2], 1), a0 = __shfl_down_sync(full, v[0], 2);
-    float b5 = __shfl_up_sync(full, v[5], 1), b6 = __shfl_up_sync(full, v[6], 1);
-    float n0 = __shfl_down_sync(full, v[0], 1);                 // lane 1's v0, needed by lane 0 (spill to fine -1)
-    float x0 = v[3], x1 = v[4];
-    if (lane < 31) { x0 += a1; x1 += a2; }
-    if (lane < 30) x1 += a0;
-    if (lane > 0) { x0 += b5; x1 += b6; }
-    float* row = xs + (td * kXH + 2 * hrow + th) * kXW;
-    float2* cell = reinterpret_cast<float2*>(row + 4 + 2 * lane);
-    float2 cur = *cell;
-    cur.x += x0; cur.y += x1;
-    *cell = cur;
-    if (lane == 0) { row[1] += v[0]; row[2] += v[1]; row[3] += v[2] + n0; }
-    if (lane == 31) { row[68] += v[5]; row[69] += v[6]; }
-  }
-};
+struct EdgeMasks { float lt31, lt30, gt0; };   // 1.0 / 0.0 lane masks: fma(x, mask, acc) adds x only where the neighbour exists
 
-__device__ __forceinline__ void syn_tile_coords(const SynTcParams& p, int tile, int& n, int& qd, int& qh0, int& qw0) {
-  int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  int th = tile % p.tiles_h; tile /= p.tiles_h;
-  qd = tile % p.g.Qd; n = tile / p.g.Qd;
-  qh0 = th * 2 * kTH; qw0 = tw * kTW;
+// NR consecutive (th,td) rows R0..R0+NR-1, all inside one th group, whose taps sit in u[7*(R-RC0) .. +6].
+// Phase 1: w-direction reduction with shuffles (independent across rows), phase 2: all shared-memory loads,
+// phase 3: adds and stores - so the NR read-modify-writes overlap instead of forming one dependent chain.
+template <int R0, int NR, int RC0, int COLS>
+__device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs, int hrow, int lane, const EdgeMasks& em) {
+  constexpr int th = R0 / 7;
+  const unsigned full = 0xffffffffu;
+  float x0[NR], x1[NR], e1[NR], e2[NR], e3[NR], f5[NR], f6[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int o = 7 * (R0 + i - RC0);
+    const float v0 = __uint_as_float(u[o]), v1 = __uint_as_float(u[o + 1]), v2 = __uint_as_float(u[o + 2]),
+                v3 = __uint_as_float(u[o + 3]), v4 = __uint_as_float(u[o + 4]), v5 = __uint_as_float(u[o + 5]),
+                v6 = __uint_as_float(u[o + 6]);
+    const float a1 = __shfl_down_sync(full, v1, 1), a2 = __shfl_down_sync(full, v2, 1), a0 = __shfl_down_sync(full, v0, 2);
+    const float b5 = __shfl_up_sync(full, v5, 1), b6 = __shfl_up_sync(full, v6, 1);
+    const float n0 = __shfl_down_sync(full, v0, 1);            // lane 1's v0, used by lane 0 (spill to fine -1)
+    x0[i] = fmaf(b5, em.gt0, fmaf(a1, em.lt31, v3));           // fine w = 2q   : taps 3 (own), 1 (q+1), 5 (q-1)
+    x1[i] = fmaf(b6, em.gt0, fmaf(a0, em.lt30, fmaf(a2, em.lt31, v4)));   // fine w = 2q+1 : taps 4, 2 (q+1), 0 (q+2), 6 (q-1)
+    e1[i] = v0; e2[i] = v1; e3[i] = v2 + n0; f5[i] = v5; f6[i] = v6;
+  }
+  float* rowp[NR];
+  float2 cur[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const int td = (R0 + i) % 7;
+    rowp[i] = xs + (td * kXH + 2 * hrow + th) * kXW;
+    cur[i] = *reinterpret_cast<const float2*>(rowp[i] + 4 + 2 * lane);
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    cur[i].x += x0[i]; cur[i].y += x1[i];
+    *reinterpret_cast<float2*>(rowp[i] + 4 + 2 * lane) = cur[i];
+  }
+  if (lane == 0) {                                  // left spill: fine w = 2*qw0 - 3 .. -1  (tile columns 1..3)
+    float4 q[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) q[i] = *reinterpret_cast<const float4*>(rowp[i]);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      q[i].y += e1[i]; q[i].z += e2[i]; q[i].w += e3[i];
+      *reinterpret_cast<float4*>(rowp[i]) = q[i];
+    }
+  }
+  if (lane == 31) {                                 // right spill: fine w = 2*qw0 + 64, 65  (tile columns 68, 69)
+    float2 q[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) q[i] = *reinterpret_cast<const float2*>(rowp[i] + 68);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      q[i].x += f5[i]; q[i].y += f6[i];
+      *reinterpret_cast<float2*>(rowp[i] + 68) = q[i];
+    }
+  }
 }
 
-// compile-time walk over the columns of accumulator chunk NC: column J holds tap t' = 64*NC + J
-template <int NC, int J, int COLS>
-struct ChunkStep {
-  static __device__ __forceinline__ void run(const uint32_t (&u)[COLS], float (&rowv)[7], float* xs, int hrow, int lane) {
-    constexpr int t = NC * 64 + J;
-    if constexpr (t < kTaps) {
-      rowv[t % 7] = __uint_as_float(u[J]);
-      if constexpr (t % 7 == 6) {
-        // lock step over th: every warp finishes th-group g before any starts g+1
-        if constexpr ((t / 7) % 7 == 0 && (t / 49) > 0) ptx::named_bar_sync(2, 128);
-        RowOps<t / 7>::apply(rowv, xs, hrow, lane);
-      }
-    }
-    if constexpr (J + 1 < COLS) ChunkStep<NC, J + 1, COLS>::run(u, rowv, xs, hrow, lane);
+// rows [R, REND) of the chunk that starts at row RC0, split at th-group boundaries; warps run the th groups in lock
+// step (named barrier 2) so that no two warps ever touch the same shared-memory row at the same time
+template <int R, int REND, int RC0, int COLS>
+__device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, int hrow, int lane, const EdgeMasks& em) {
+  if constexpr (R < REND) {
+    constexpr int RB = ((R / 7) + 1) * 7 < REND ? ((R / 7) + 1) * 7 : REND;
+    if constexpr (R % 7 == 0 && R > 0) ptx::named_bar_sync(2, 128);
+    rows_apply<R, RB - R, RC0, COLS>(u, xs, hrow, lane, em);
+    rows_walk<RB, REND, RC0, COLS>(u, xs, hrow, lane, em);
   }
-};
+}
 
 template <int NC>
-__device__ __forceinline__ void syn_epilogue_chunk(uint32_t taddr, float (&rowv)[7], float* xs, int hrow, int lane,
+__device__ __forceinline__ void syn_epilogue_chunk(uint32_t taddr, float* xs, int hrow, int lane, const EdgeMasks& em,
                                                    uint64_t* dempty_slot, uint64_t* dfull_slot, uint32_t parity) {
   using namespace ptx;
   constexpr int COLS = NC < 5 ? 64 : 32;
@@ -140,7 +166,14 @@ __device__ __forceinline__ void syn_epilogue_chunk(uint32_t taddr, float (&rowv)
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(dempty_slot, 0);           // accumulator slot is free again
-  ChunkStep<NC, 0, COLS>::run(u, rowv, xs, hrow, lane);
+  rows_walk<NC * kRowsPerChunk, NC * kRowsPerChunk + syn_chunk_nrows(NC), NC * kRowsPerChunk, COLS>(u, xs, hrow, lane, em);
+}
+
+__device__ __forceinline__ void syn_tile_coords(const SynTcParams& p, int tile, int& n, int& qd, int& qh0, int& qw0) {
+  int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  int th = tile % p.tiles_h; tile /= p.tiles_h;
+  qd = tile % p.g.Qd; n = tile / p.g.Qd;
+  qh0 = th * 2 * kTH; qw0 = tw * kTW;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_synthesis(const SynTcParams p) {
@@ -188,6 +221,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     // warp = 4*half + quad: TMEM lanes of tile row `quad`, subbands [88*half, 88*half+88)
     const int quad = warp & 3, half = warp >> 2;
     const int m0 = half * (kKB / 2);
+    const int mcount = min(kKB / 2, max(0, g.M - m0));
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
@@ -204,27 +238,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
         const int qh2 = qh02 + rank * kTH + quad;
         if (qh2 < g.Qh) {
           const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02;
-          for (int m = m0 + lane; m < m0 + kKB / 2 && m < g.M; m += 32) prefetch_l2(z2 + m * mstride);
+          for (int m = lane; m < mcount; m += 32) prefetch_l2(z2 + (size_t)(m0 + m) * mstride);
         }
       }
       const uint32_t acol = lane_addr + kColA0 + ab * kKB + m0;
+      const int cnt = valid ? mcount : 0;
       uint32_t v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((valid && m0 + i < g.M) ? __ldg(zq + i * mstride) : 0.0f);
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((i < cnt) ? __ldg(zq + i * mstride) : 0.0f);
       mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1);     // first batch is in flight while the MMAs still read this buffer
       tc_fence_after();
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
       tmem_st32(acol, v);
+      {
+        const float* pz = zq + (size_t)32 * mstride;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((valid && m0 + 32 + i < g.M) ? __ldg(zq + (32 + i) * mstride) : 0.0f);
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((i + 32 < cnt) ? __ldg(pz + i * mstride) : 0.0f);
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
       tmem_st32(acol + 32, v);
       {
         uint32_t w[24];
+        const float* pz = zq + (size_t)64 * mstride;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) w[i] = __float_as_uint((valid && m0 + 64 + i < g.M) ? __ldg(zq + (64 + i) * mstride) : 0.0f);
+        for (int i = 0; i < 24; ++i) w[i] = __float_as_uint((i + 64 < cnt) ? __ldg(pz + i * mstride) : 0.0f);
 #pragma unroll
         for (int i = 0; i < 24; ++i) w[i] = __float_as_uint(to_tf32_rna(__uint_as_float(w[i])));
         tmem_st16(acol + 64, *reinterpret_cast<const uint32_t(*)[16]>(&w[0]));
@@ -240,14 +279,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     const int ew = warp - 8;
     const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
     const int et = tid - 256;
+    const EdgeMasks em = {lane < 31 ? 1.0f : 0.0f, lane < 30 ? 1.0f : 0.0f, lane > 0 ? 1.0f : 0.0f};
     uint32_t gch = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs) {
-      float rowv[7];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) rowv[i] = 0.0f;
-      // six accumulator chunks, ring of 2 slots
+      // six accumulator chunks (9,9,9,9,9,4 rows of 7 taps), ring of 2 slots
 #define CDL_CHUNK(NC) { const uint32_t s_ = gch & 1; \
-        syn_epilogue_chunk<NC>(lane_addr + kColDB + s_ * kDSlot, rowv, sX, ew, lane, &dempty[s_], &dfull[s_], (gch >> 1) & 1); ++gch; }
+        syn_epilogue_chunk<NC>(lane_addr + kColDB + s_ * kDSlot, sX, ew, lane, em, &dempty[s_], &dfull[s_], (gch >> 1) & 1); ++gch; }
       CDL_CHUNK(0) CDL_CHUNK(1) CDL_CHUNK(2) CDL_CHUNK(3) CDL_CHUNK(4) CDL_CHUNK(5)
 #undef CDL_CHUNK
       named_bar_sync(2, 128);                    // footprint complete
