@@ -230,39 +230,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
           for (int m = lane; m < mcount; m += 32) prefetch_l2(z2 + m * mstride);
         }
       }
+      const long long msb = (long long)mstride * 4;              // byte stride between subbands
       float zc[16];
       {
-        const float* pz = zq;
+        const char* a = reinterpret_cast<const char*>(zq);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) zc[i] = (i < cnt_ld) ? __ldg(pz + i * mstride) : 0.0f;   // batch 0, before the accumulator is ready
+        for (int i = 0; i < 16; ++i, a += msb) zc[i] = ldg_f32_pred(a, i < cnt_ld);   // batch 0, before the accumulator is ready
       }
       mbar_wait(&dfull[ds], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
+      char* zb = reinterpret_cast<char*>(zq);
 #pragma unroll 1
-      for (int b = 0; b < 5; ++b) {
+      for (int b = 0; b < 5; ++b, zb += 16 * msb) {
         uint32_t u[16];
         tmem_ld16(dcol + b * 16, u);
         float zn[16];
         {
-          const float* pz = zq + (size_t)(b + 1) * 16 * mstride;
+          const char* a = zb + 16 * msb;
           const int c2 = cnt_ld - (b + 1) * 16;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) zn[i] = (i < c2) ? __ldg(pz + i * mstride) : 0.0f;     // next batch in flight
+          for (int i = 0; i < 16; ++i, a += msb) zn[i] = ldg_f32_pred(a, i < c2);     // next batch in flight
         }
         tmem_wait_ld();
-        float* po = zq + (size_t)b * 16 * mstride;
         const int c1 = cnt - b * 16;
         const float4* tq = reinterpret_cast<const float4*>(sTau + m0 + b * 16);
+        char* a = zb;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const float4 t4 = tq[i4];
           const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 4; ++j, a += msb) {
             const int i = i4 * 4 + j;
             const float v = __fsub_rn(zc[i], __uint_as_float(u[i] ^ usign));
-            if (i < c1) po[i * mstride] = soft_threshold(v, tt[j]);
+            stg_f32_pred(a, soft_threshold(v, tt[j]), i < c1);
           }
         }
 #pragma unroll
@@ -275,12 +277,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         tc_fence_before();                         // accumulator fully read: hand the TMEM slot back to the MMA warp
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&dempty[ds], 0);
-        float* po = zq + (size_t)80 * mstride;
         const int c1 = cnt - 80;
+        char* a = zb;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i, a += msb) {
           const float v = __fsub_rn(zc[i], __uint_as_float(u[i] ^ usign));
-          if (i < c1) po[i * mstride] = soft_threshold(v, sTau[m0 + 80 + i]);
+          stg_f32_pred(a, soft_threshold(v, sTau[m0 + 80 + i]), i < c1);
         }
       }
     }

@@ -172,6 +172,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// predicated streaming load (0 when !ok) / store: one instruction each, no branch region, explicit address
+__device__ __forceinline__ float ldg_f32_pred(const char* addr, int ok) {
+  float v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.global.nc.L1::no_allocate.f32 %0, [%1];\n\t}"
+               : "=f"(v) : "l"(addr), "r"(ok));
+  return v;
+}
+__device__ __forceinline__ void stg_f32_pred(char* addr, float v, int ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(ok) : "memory");
+}
 __device__ __forceinline__ float to_tf32_rna(float x) {   // round-to-nearest (ties away) to 10-bit mantissa
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

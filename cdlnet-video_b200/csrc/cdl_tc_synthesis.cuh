@@ -243,27 +243,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       }
       const uint32_t acol = lane_addr + kColA0 + ab * kKB + m0;
       const int cnt = valid ? mcount : 0;
+      const long long msb = (long long)mstride * 4;
+      const char* a = reinterpret_cast<const char*>(zq);
       uint32_t v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((i < cnt) ? __ldg(zq + i * mstride) : 0.0f);
+      for (int i = 0; i < 32; ++i, a += msb) v[i] = __float_as_uint(ldg_f32_pred(a, i < cnt));
       mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1);     // first batch is in flight while the MMAs still read this buffer
       tc_fence_after();
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
       tmem_st32(acol, v);
-      {
-        const float* pz = zq + (size_t)32 * mstride;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((i + 32 < cnt) ? __ldg(pz + i * mstride) : 0.0f);
-      }
+      for (int i = 0; i < 32; ++i, a += msb) v[i] = __float_as_uint(ldg_f32_pred(a, i + 32 < cnt));
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
       tmem_st32(acol + 32, v);
       {
         uint32_t w[24];
-        const float* pz = zq + (size_t)64 * mstride;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) w[i] = __float_as_uint((i + 64 < cnt) ? __ldg(pz + i * mstride) : 0.0f);
+        for (int i = 0; i < 24; ++i, a += msb) w[i] = __float_as_uint(ldg_f32_pred(a, i + 64 < cnt));
 #pragma unroll
         for (int i = 0; i < 24; ++i) w[i] = __float_as_uint(to_tf32_rna(__uint_as_float(w[i])));
         tmem_st16(acol + 64, *reinterpret_cast<const uint32_t(*)[16]>(&w[0]));
