@@ -32,6 +32,36 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+// ---- TMA tensor map of a fine (N,1,Fd,Fh,Fw) fp32 volume: box 72 x 13 x 7 x 1, zero fill out of bounds ----
+typedef CUresult (*cdl_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cdl_encode_tiled_fn g_encode_tiled = nullptr;
+static int load_encode_tiled() {
+  if (g_encode_tiled) return CDL_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return CDL_CUDA_ERROR_BASE + (int)e;
+  if (!fn || q != cudaDriverEntryPointSuccess) return CDL_ERR_NO_DEVICE;
+  g_encode_tiled = (cdl_encode_tiled_fn)fn;
+  return CDL_OK;
+}
+static int make_fine_tmap(CUtensorMap* out, const float* base, const Geo& g) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)g.Fw, (cuuint64_t)g.Fh, (cuuint64_t)g.Fd, (cuuint64_t)g.N};
+  const cuuint64_t gstr[3] = {(cuuint64_t)g.Fw * 4, (cuuint64_t)g.Fw * g.Fh * 4, (cuuint64_t)g.Fw * g.Fh * g.Fd * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)tc::kRW, (cuuint32_t)tc::kRH, (cuuint32_t)tc::kRD, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CDL_OK : CDL_ERR_UNSUPPORTED;
+}
+
+// development aid (not part of the ABI): cycle counters of the tensor-core kernels' warp roles
+static long long* g_tc_dbg = nullptr;
+extern "C" void cdl__debug_set_buffer(long long* p) { g_tc_dbg = p; }
+
 struct cdl_plan {
   cdl_desc_t desc;
   Geo g;
@@ -297,6 +327,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     return CDL_CUDA_ERROR_BASE + (int)e;
   }
   if (p->tc_ana) {
+    { int rc = load_encode_tiled(); if (rc) { cdl_plan_destroy(p); return rc; } }
     p->wAtc_layer = 2 * (size_t)tc::kKSteps * tc::kNAH * 8;
     int dev_sms = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device);
@@ -497,9 +528,12 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     a.tiles_w = ceil_div(p->g.Qw, tc::kTW);
     a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
+    a.dbg = g_tc_dbg;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
-    tc::k_tc_analysis<<<2 * pairs, tc::kThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a);
+    CUtensorMap rmap;
+    { int rc = make_fine_tmap(&rmap, r, p->g); if (rc) return rc; }
+    tc::k_tc_analysis<<<2 * pairs, tc::kThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a, rmap);
     CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }
@@ -545,6 +579,7 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.tiles_w = ceil_div(p->g.Qw, tc::kTW);
     a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
+    a.dbg = g_tc_dbg;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
     tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);

@@ -36,7 +36,8 @@ constexpr int kChunkRows = 8;            // (td,th) rows per A chunk -> 56 colum
 constexpr int kChunks = 7;               // 6 full chunks + 1 chunk of one row (7 taps + 1 zero column)
 constexpr int kTH = 4, kTW = 32;         // coarse tile per CTA: 1 x 4 x 32 (d,h,w); a pair stacks two along h
 constexpr int kRD = 7, kRH = 2 * (kTH - 1) + kP, kRW = 72;   // residual halo tile (fine): 7 x 13 x 72 floats
-constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats
+constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats = 26208 B (one TMA box)
+constexpr int kRTilePad = 6560;          // buffer pitch: 26240 B, a multiple of 128 B (TMA destination alignment)
 constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 64;   // TMEM columns: D0 | D1 | A0 | A1  (480 of 512)
 
 struct AnaTcParams {
@@ -50,10 +51,11 @@ struct AnaTcParams {
   int first;
   int tiles_w, tiles_h; // pair tiles along w (32 sites) and h (8 rows)
   int ntiles;           // N * Qd * tiles_h * tiles_w
+  long long* dbg;       // optional [grid][16 warps][8] cycle counters
 };
 
 constexpr size_t kAnaSmemB = (size_t)kKSteps * kNAH * 8 * sizeof(float);      // 121088
-constexpr size_t kAnaSmemR = 2 * (size_t)kRTile * sizeof(float);              // 52416
+constexpr size_t kAnaSmemR = 2 * (size_t)kRTilePad * sizeof(float);           // 52480
 constexpr size_t kAnaSmemT = 2 * kNA * sizeof(float);                         // thresholds t0 | t1
 constexpr size_t kAnaSmemBytes = kAnaSmemB + kAnaSmemR + kAnaSmemT + 256;
 
@@ -76,7 +78,7 @@ __device__ __forceinline__ void ana_tile_coords(const AnaTcParams& p, int tile, 
   qh0 = th * 2 * kTH; qw0 = tw * kTW;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_analysis(const AnaTcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_analysis(const AnaTcParams p, const __grid_constant__ CUtensorMap rmap) {
   using namespace ptx;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* sB = reinterpret_cast<float*>(smem_raw);
@@ -89,16 +91,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
   uint64_t* dfull = bars + 5;    // [2]  MMA commit (multicast) -> epilogue
   uint64_t* dempty = bars + 7;   // [2]  (leader) epilogue warps of both CTAs -> MMA
   uint64_t* wready = bars + 9;   //      (leader) the peer CTA's filters have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* rfull = bars + 10;   // [2]  TMA: residual halo tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0;
+  const long long tstart = clock64();
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&rfull[i], 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 16); }
     fence_mbar_init();
   }
@@ -122,40 +128,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
   if (warp < 4) {
     // ============================== producers: r tile -> im2col -> TMEM ==============================
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    // one thread per CTA drives the TMA: box 72 x 13 x 7 (w,h,d) of r with zero fill outside the clip = the conv's padding
     auto issue_tile_load = [&](int tile, int buf) {
       int n, qd, qh0, qw0;
       ana_tile_coords(p, tile, n, qd, qh0, qw0);
       qh0 += rank * kTH;
-      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;      // tile column 0 <-> fine w = 2*qw0 - 4 (16-B aligned)
-      float* dst = sR + buf * kRTile;
-      const float* src_n = p.rin + (size_t)n * g.fine_vol();
-      for (int row = warp; row < kRD * kRH; row += 4) {
-        const int d = row / kRH, h = row % kRH;
-        const int gd = fd0 + d, gh = fh0 + h;
-        const bool row_ok = gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh;
-        if (lane < kRW / 4) {
-          const int gw = fw0 + 4 * lane;
-          const bool ok = row_ok && gw >= 0 && gw + 4 <= g.Fw;
-          const float* src = ok ? src_n + ((size_t)gd * g.Fh + gh) * g.Fw + gw : p.rin;
-          cp_async16_zfill(dst + row * kRW + 4 * lane, src, ok);
-        }
-      }
-      cp_async_commit();
+      mbar_expect_tx(&rfull[buf], kRTile * 4);
+      tma_load_4d(sR + buf * kRTilePad, &rmap, 2 * qw0 - 4, 2 * qh0 - 3, 2 * qd - g.od, n, &rfull[buf]);   // column 0 <-> fine w = 2*qw0 - 4
     };
     int it = 0;
     uint32_t gchunk = 0;
-    if (pair < p.ntiles) issue_tile_load(pair, 0);
+    if (tid == 0) { tma_prefetch_desc(&rmap); if (pair < p.ntiles) issue_tile_load(pair, 0); }
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       const int buf = it & 1;
-      cp_async_wait<0>();
-      named_bar_sync(1, 128);                       // tile `it` landed for everyone; everyone left tile it-1
-      if (tile + npairs < p.ntiles) issue_tile_load(tile + npairs, buf ^ 1);
+      CDL_TW(tw1, mbar_wait(&rfull[buf], (it >> 1) & 1); named_bar_sync(1, 128));   // tile `it` landed; everyone left tile it-1
+      if (tid == 0 && tile + npairs < p.ntiles) issue_tile_load(tile + npairs, buf ^ 1);
       // this thread's coarse site: row `warp` of the CTA tile, column `lane`
-      const float* rs = sR + buf * kRTile + (2 * warp) * kRW + 2 * lane;
+      const float* rs = sR + buf * kRTilePad + (2 * warp) * kRW + 2 * lane;
 #pragma unroll
       for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
         const uint32_t slot = gchunk & 1;
-        mbar_wait(&aempty[slot], ((gchunk >> 1) & 1) ^ 1);
+        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gchunk >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t acol = lane_addr + kColA + slot * kASlot;
         if (ch < kChunks - 1) {
@@ -186,10 +179,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
           v[6] = __float_as_uint(to_tf32_rna(d.y)); v[7] = 0u;
           tmem_st8(acol, v);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&afull[slot], 0);
+        CDL_TW(tw2, tmem_wait_st());
+        CDL_TW(tw4, tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
       }
     }
   } else if (warp < kMmaWarp) {
@@ -237,7 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
 #pragma unroll
         for (int i = 0; i < 16; ++i, a += msb) zc[i] = ldg_f32_pred(a, i < cnt_ld);   // batch 0, before the accumulator is ready
       }
-      mbar_wait(&dfull[ds], (it >> 1) & 1);
+      CDL_TW(tw0, mbar_wait(&dfull[ds], (it >> 1) & 1));
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
       char* zb = reinterpret_cast<char*>(zq);
@@ -276,7 +267,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         tmem_wait_ld();
         tc_fence_before();                         // accumulator fully read: hand the TMEM slot back to the MMA warp
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&dempty[ds], 0);
+        if (lane == 0) { if (rank == 0) mbar_arrive(&dempty[ds]); else mbar_arrive_cluster(&dempty[ds], 0); }
         const int c1 = cnt - 80;
         char* a = zb;
 #pragma unroll
@@ -290,26 +281,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
     // ============================== MMA issue (leader CTA, one thread) ==============================
     if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0 && lane == 0) {
-      mbar_wait(wbar, 0);
-      mbar_wait_cluster(wready, 0);
+      CDL_TW(tw2, mbar_wait(wbar, 0); mbar_wait_cluster(wready, 0));
       const uint32_t idesc = make_idesc_tf32(256, kNA);
-      const uint32_t sB_addr = smem_u32(sB);
+      const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
+      constexpr uint32_t kBStep = (kNAH * 32) >> 4;                 // 16-byte units between consecutive k-steps of B
       int it = 0;
       uint32_t gchunk = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
         const uint32_t ds = it & 1;
-        mbar_wait_cluster(&dempty[ds], ((it >> 1) & 1) ^ 1);
+        CDL_TW(tw0, mbar_wait_cluster(&dempty[ds], ((it >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t dcol = tbase + kColD + ds * kNA;
         for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
           const uint32_t slot = gchunk & 1;
-          mbar_wait_cluster(&afull[slot], (gchunk >> 1) & 1);
+          CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gchunk >> 1) & 1));
           tc_fence_after();
-          const int nsteps = (ch < kChunks - 1) ? 7 : 1;
-          for (int j = 0; j < nsteps; ++j) {
-            const int ks = ch * 7 + j;
-            const uint64_t bdesc = make_smem_desc_kmajor_noswz(sB_addr + ks * (kNAH * 32), 128, 256);
-            mma_tf32_ts<2>(dcol, tbase + kColA + slot * kASlot + j * 8, bdesc, idesc, ks > 0);
+          const uint32_t a0 = tbase + kColA + slot * kASlot;
+          uint64_t bdesc = bdesc0 + (uint64_t)(ch * 7) * kBStep;      // descriptor start-address field advances by kBStep per k-step
+          if (ch < kChunks - 1) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bdesc + (uint64_t)j * kBStep, idesc, (ch | j) != 0);
+          } else {
+            mma_tf32_ts<2>(dcol, a0, bdesc, idesc, 1);
           }
           mma_commit<2>(&aempty[slot]);             // A slot reusable once these MMAs have read it
         }
@@ -317,6 +310,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
       }
     }
     __syncwarp();                                   // reconverge the MMA warp before the aligned cluster barrier
+  }
+  if (p.dbg && lane == 0) {
+    long long* d = p.dbg + ((size_t)blockIdx.x * 16 + warp) * 8;
+    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2; d[4] = tw3; d[5] = tw4;
   }
   // teardown: everyone done (all MMAs were consumed by the epilogues before they exit)
   tc_fence_before();

@@ -1,8 +1,12 @@
 // cdl_tc_ptx.cuh — thin inline-PTX wrappers for the sm_100a tensor-core path: tcgen05 (MMA, TMEM
 // alloc / ld / st / commit / fences), mbarrier, cluster barrier, bulk async copy.  No CUTLASS.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+// development aid: per-warp cycle counters of the barrier waits (enabled when a debug buffer is set)
+#define CDL_TW(acc, stmt) do { long long t0__ = clock64(); stmt; acc += clock64() - t0__; } while (0)
 
 namespace cdl {
 namespace ptx {
@@ -161,6 +165,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA: 4-D tiled tensor load global -> shared, out-of-bounds elements are written as zero; completion (full box
+// bytes) is signalled on the mbarrier.  `map` must live in kernel-parameter (__grid_constant__) or global memory.
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
+// 16-byte vector reduction (sm_90+): out[0..3] += v
+__device__ __forceinline__ void red_add_v4_f32(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // 16-byte cp.async with zero-fill when !valid (src must still be a mapped address)
 __device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {

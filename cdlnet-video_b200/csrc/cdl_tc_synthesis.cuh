@@ -40,6 +40,7 @@ struct SynTcParams {
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
   const float* wpack;   // this layer: [2 ranks][chunk][22 k-steps][rows/8][2][8][4]
   int tiles_w, tiles_h, ntiles;
+  long long* dbg;
 };
 
 __host__ __device__ constexpr int syn_chunk_rows(int nc) { return nc < 5 ? 32 : 16; }          // B rows per CTA in chunk nc
@@ -47,7 +48,7 @@ constexpr int kRowsPerChunk = 9;                                                
 __host__ __device__ constexpr int syn_chunk_nrows(int nc) { return nc < 5 ? 9 : 4; }
 __host__ __device__ constexpr int syn_chunk_off(int nc) { return nc * (kKBSteps * 32 * 8); }   // float offset of chunk nc
 constexpr size_t kSynSmemB = (size_t)(5 * 32 + 16) * kKB * sizeof(float);                      // 123904
-constexpr size_t kSynSmemX = (size_t)kXTile * sizeof(float);                                   // 26208
+constexpr size_t kSynSmemX = 2 * (size_t)kXTile * sizeof(float);                               // two footprint tiles, 52416
 constexpr size_t kSynSmemBytes = kSynSmemB + kSynSmemX + 256;
 
 // filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[n = t' = (th,td,tw), k = m], per-rank UMMA layout, tf32 RNE
@@ -155,17 +156,17 @@ __device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, 
 
 template <int NC>
 __device__ __forceinline__ void syn_epilogue_chunk(uint32_t taddr, float* xs, int hrow, int lane, const EdgeMasks& em,
-                                                   uint64_t* dempty_slot, uint64_t* dfull_slot, uint32_t parity) {
+                                                   uint64_t* dempty_slot, uint64_t* dfull_slot, uint32_t parity, long long& tw, uint32_t rank) {
   using namespace ptx;
   constexpr int COLS = NC < 5 ? 64 : 32;
-  mbar_wait(dfull_slot, parity);
+  CDL_TW(tw, mbar_wait(dfull_slot, parity));
   tc_fence_after();
   uint32_t u[COLS];
   if constexpr (COLS == 64) tmem_ld64(taddr, u); else tmem_ld32(taddr, u);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(dempty_slot, 0);           // accumulator slot is free again
+  if (lane == 0) { if (rank == 0) mbar_arrive(dempty_slot); else mbar_arrive_cluster(dempty_slot, 0); }   // accumulator slot is free again
   rows_walk<NC * kRowsPerChunk, NC * kRowsPerChunk + syn_chunk_nrows(NC), NC * kRowsPerChunk, COLS>(u, xs, hrow, lane, em);
 }
 
@@ -188,21 +189,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   uint64_t* dfull = bars + 5;    // [2] MMA commit (multicast) -> epilogue
   uint64_t* dempty = bars + 7;   // [2] (leader) epilogue warps of both CTAs -> MMA
   uint64_t* wready = bars + 9;   //     (leader) the peer CTA's filters have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* xfull = bars + 10;   // [2] epilogue -> producers: footprint tile complete, flush it
+  uint64_t* xfree = bars + 12;   // [2] producers -> epilogue: footprint tile flushed and cleared
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  long long tw0 = 0, tw1 = 0, tw2 = 0;
+  const long long tstart = clock64();
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 4); mbar_init(&xfree[i], 8); }
     for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
-  for (int i = tid; i < kXTile; i += kThreads) sX[i] = 0.0f;
+  for (int i = tid; i < 2 * kXTile; i += kThreads) sX[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(wbar, (uint32_t)kSynSmemB);
@@ -223,6 +229,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     const int m0 = half * (kKB / 2);
     const int mcount = min(kKB / 2, max(0, g.M - m0));
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
+    // out[fine] += footprint of tile `t` (the j-th tile of this CTA), then clear the buffer for tile j+2.
+    // Done by the 256 producer threads so the col2im warps can move straight on to the next tile.
+    auto flush_tile = [&](int t, int j) {
+      const int xb = j & 1;
+      CDL_TW(tw1, mbar_wait(&xfull[xb], (j >> 1) & 1));
+      int n, qd, qh0, qw0;
+      syn_tile_coords(p, t, n, qd, qh0, qw0);
+      qh0 += rank * kTH;
+      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;
+      float* on = p.out + (size_t)n * g.fine_vol();
+      float* xs = sX + xb * kXTile;
+      for (int r = warp; r < kXD * kXH; r += 8) {                // one 72-float row per warp pass, 18 float4 per row
+        const int h = r % kXH, d = r / kXH;
+        const int gd = fd0 + d, gh = fh0 + h, gw = fw0 + 4 * lane;
+        if (lane < kXW / 4) {
+          float4* cell = reinterpret_cast<float4*>(xs + r * kXW + 4 * lane);
+          const float4 v = *cell;
+          *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh && gw >= 0 && gw + 4 <= g.Fw)
+            red_add_v4_f32(on + ((size_t)gd * g.Fh + gh) * g.Fw + gw, v);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfree[xb]);
+    };
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       const uint32_t ab = it & 1;
@@ -248,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       uint32_t v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i, a += msb) v[i] = __float_as_uint(ldg_f32_pred(a, i < cnt));
-      mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1);     // first batch is in flight while the MMAs still read this buffer
+      CDL_TW(tw0, mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1));     // first batch is in flight while the MMAs still read this buffer
       tc_fence_after();
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
@@ -270,8 +301,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&afull[ab], 0);
+      if (lane == 0) { if (rank == 0) mbar_arrive(&afull[ab]); else mbar_arrive_cluster(&afull[ab], 0); }
+      if (it > 0) flush_tile(tile - npairs, it - 1);
     }
+    if (it > 0) flush_tile(pair + (it - 1) * npairs, it - 1);      // footprint of the last tile
   } else if (warp < kMmaWarp) {
     // ============================== epilogue: col2im ==============================
     const int ew = warp - 8;
@@ -279,60 +312,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     const int et = tid - 256;
     const EdgeMasks em = {lane < 31 ? 1.0f : 0.0f, lane < 30 ? 1.0f : 0.0f, lane > 0 ? 1.0f : 0.0f};
     uint32_t gch = 0;
-    for (int tile = pair; tile < p.ntiles; tile += npairs) {
+    int it = 0;
+    for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+      const int xb = it & 1;
+      float* xs = sX + xb * kXTile;
+      CDL_TW(tw1, mbar_wait(&xfree[xb], ((it >> 1) & 1) ^ 1));      // footprint buffer flushed + cleared (first two uses pass)
       // six accumulator chunks (9,9,9,9,9,4 rows of 7 taps), ring of 2 slots
 #define CDL_CHUNK(NC) { const uint32_t s_ = gch & 1; \
-        syn_epilogue_chunk<NC>(lane_addr + kColDB + s_ * kDSlot, sX, ew, lane, em, &dempty[s_], &dfull[s_], (gch >> 1) & 1); ++gch; }
+        syn_epilogue_chunk<NC>(lane_addr + kColDB + s_ * kDSlot, xs, ew, lane, em, &dempty[s_], &dfull[s_], (gch >> 1) & 1, tw0, rank); ++gch; }
       CDL_CHUNK(0) CDL_CHUNK(1) CDL_CHUNK(2) CDL_CHUNK(3) CDL_CHUNK(4) CDL_CHUNK(5)
 #undef CDL_CHUNK
-      named_bar_sync(2, 128);                    // footprint complete
-      // flush: out[fine] += tile, then clear the tile for the next round
-      int n, qd, qh0, qw0;
-      syn_tile_coords(p, tile, n, qd, qh0, qw0);
-      qh0 += rank * kTH;
-      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;
-      float* on = p.out + (size_t)n * g.fine_vol();
-      for (int i = et; i < kXD * kXH * (kXW / 4); i += 128) {
-        const int c4 = i % (kXW / 4), r = i / (kXW / 4);
-        const int h = r % kXH, d = r / kXH;
-        const int gd = fd0 + d, gh = fh0 + h, gw = fw0 + 4 * c4;
-        float4* cell = reinterpret_cast<float4*>(sX + r * kXW + 4 * c4);
-        const float4 v = *cell;
-        *cell = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh && gw >= 0 && gw + 4 <= g.Fw) {
-          float* dst = on + ((size_t)gd * g.Fh + gh) * g.Fw + gw;
-          if (v.x != 0.f) red_add_f32(dst + 0, v.x);
-          if (v.y != 0.f) red_add_f32(dst + 1, v.y);
-          if (v.z != 0.f) red_add_f32(dst + 2, v.z);
-          if (v.w != 0.f) red_add_f32(dst + 3, v.w);
-        }
-      }
-      named_bar_sync(2, 128);                    // tile cleared before the next round's first add
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfull[xb]);      // this warp's rows are in; 4 arrivals -> producers flush the tile
+      named_bar_sync(2, 128);                      // th lock step restarts with everyone at group 0
     }
   } else {
     // ============================== MMA issue (leader CTA, one thread) ==============================
     if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0 && lane == 0) {
-      mbar_wait(wbar, 0);
-      mbar_wait_cluster(wready, 0);
-      const uint32_t sB_addr = smem_u32(sB);
+      CDL_TW(tw2, mbar_wait(wbar, 0); mbar_wait_cluster(wready, 0));
+      const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
+      const uint32_t idesc64 = make_idesc_tf32(256, 64), idesc32 = make_idesc_tf32(256, 32);
       int it = 0;
       uint32_t gch = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
         const uint32_t ab = it & 1;
-        mbar_wait_cluster(&afull[ab], (it >> 1) & 1);
+        CDL_TW(tw1, mbar_wait_cluster(&afull[ab], (it >> 1) & 1));
         tc_fence_after();
         const uint32_t acol = tbase + kColA0 + ab * kKB;
         for (int nc = 0; nc < kNChunks; ++nc, ++gch) {
           const uint32_t s = gch & 1;
-          mbar_wait_cluster(&dempty[s], ((gch >> 1) & 1) ^ 1);
+          CDL_TW(tw0, mbar_wait_cluster(&dempty[s], ((gch >> 1) & 1) ^ 1));
           tc_fence_after();
-          const int rows = syn_chunk_rows(nc);
-          const uint32_t idesc = make_idesc_tf32(256, 2 * rows);
-          const uint32_t boff = sB_addr + syn_chunk_off(nc) * 4;
-          for (int ks = 0; ks < kKBSteps; ++ks) {
-            const uint64_t bdesc = make_smem_desc_kmajor_noswz(boff + ks * rows * 32, 128, 256);
-            mma_tf32_ts<2>(tbase + kColDB + s * kDSlot, acol + ks * 8, bdesc, idesc, ks > 0);
+          const uint32_t dcol = tbase + kColDB + s * kDSlot;
+          if (nc < 5) {
+            const uint64_t bd = bdesc0 + (uint64_t)nc * ((kKBSteps * 32 * 32) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < kKBSteps; ++ks) mma_tf32_ts<2>(dcol, acol + ks * 8, bd + (uint64_t)ks * ((32 * 32) >> 4), idesc64, ks > 0);
+          } else {
+            const uint64_t bd = bdesc0 + (uint64_t)5 * ((kKBSteps * 32 * 32) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < kKBSteps; ++ks) mma_tf32_ts<2>(dcol, acol + ks * 8, bd + (uint64_t)ks * ((16 * 32) >> 4), idesc32, ks > 0);
           }
           mma_commit<2>(&dfull[s]);
         }
@@ -340,6 +360,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       }
     }
     __syncwarp();
+  }
+  if (p.dbg && lane == 0) {
+    long long* d = p.dbg + ((size_t)blockIdx.x * 16 + warp) * 8;
+    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2;
   }
   tc_fence_before();
   cluster_sync_all();

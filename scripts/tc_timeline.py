@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Development aid: per-warp-role cycle accounting of the tcgen05 kernels (uses the undocumented
+cdl__debug_set_buffer hook).  Run on the GPU box:  python scripts/tc_timeline.py [clips]"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import cdlnet_video_b200 as cb
+
+clips = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+d = torch.device("cuda", 0)
+K, M = bench.CFG["K"], bench.CFG["M"]
+plan = cb.Plan(3, clips, 1, M, K, bench.CLIP, (7, 7, 7), 2, precision="tf32")
+A, B, u = bench.synthetic_weights(torch, d)
+plan.set_weights(A, B, torch.rand(K, 2, M, device=d) * 0.01)
+clean, y = bench.synthetic_clip(torch, clips, 0, d)
+c = torch.full((clips,), 25 / 255.0, device=d)
+yp, _, mean = plan.preprocess(y)
+z = torch.empty(plan.z_shape, device=d)
+r = torch.empty_like(yp)
+plan.analysis_step(0, yp, z, c, first=True)
+for k in range(1, 4):
+    plan.synthesis_step(k, z, r, yp, None, residual=True)
+    plan.analysis_step(k, r, z, c)
+torch.cuda.synchronize()
+lib = cb.load_library()
+dbg = torch.zeros(148 * 16 * 8, dtype=torch.int64, device=d)
+lib.cdl__debug_set_buffer.argtypes = [ctypes.c_void_p]
+lib.cdl__debug_set_buffer(ctypes.c_void_p(dbg.data_ptr()))
+
+
+def show(name, roles):
+    torch.cuda.synchronize()
+    t = dbg.view(148, 16, 8).cpu().double()
+    print(f"== {name}: cycles (mean over CTAs; rank0 = even blocks)")
+    for rname, warps, labels in roles:
+        for rk in (0, 1):
+            sel = t[rk::2][:, warps, :].mean(dim=(0, 1))
+            tot = sel[0].item()
+            print(f"  {rname:9s} rank{rk}: total {tot:9.0f} | " + " | ".join(f"{lab} {sel[i + 1].item():9.0f} ({100 * sel[i + 1].item() / max(tot, 1):4.1f}%)" for i, lab in enumerate(labels)))
+    dbg.zero_()
+
+
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); plan.synthesis_step(4, z, r, yp, None, residual=True); e1.record()
+show("synthesis", [("producer", list(range(0, 8)), ["wait aempty", "-", "-"]),
+                   ("epilogue", list(range(8, 12)), ["wait dfull", "flush+bars", "-"]),
+                   ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
+print("   launch ms", e0.elapsed_time(e1))
+e0.record(); plan.analysis_step(4, r, z, c); e1.record()
+show("analysis", [("producer", list(range(0, 4)), ["wait aempty", "wait r tile", "wait::st", "issue tile load", "fence+arrive"]),
+                  ("epilogue", list(range(4, 12)), ["wait dfull", "-", "-"]),
+                  ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
+print("   launch ms", e0.elapsed_time(e1))
