@@ -241,8 +241,9 @@ def main():
     # thresholds from the 85th percentile of |A_0 yp|, using the library's own kernels
     plan.set_weights(A, B, torch.zeros(CFG["K"], 2, CFG["M"], device=dev))
     yp, _, mean = plan.preprocess(y)
-    z0 = torch.empty(plan.z_shape, device=dev)
+    z0 = plan.new_code()
     plan.analysis_step(0, yp, z0, None, first=True)
+    z0 = plan.export_code(z0)
     q = torch.quantile(z0[0].abs().reshape(CFG["M"], -1)[:, ::8].float(), 0.85, dim=1)
     t = thresholds_from_quantile(torch, q, u)
     plan.set_weights(A, B, t)
@@ -318,6 +319,7 @@ def main():
             peak_src = "fallback (B200_PROFILING.md)"
         ypb, _, meanb = plan.preprocess(y)
         r = torch.empty_like(ypb)
+        code = plan.new_code()
         acc = {"analysis": [], "synthesis": []}
 
         def timed(kind, fn):
@@ -325,11 +327,11 @@ def main():
             a.record(stream); fn(); b.record(stream)
             acc[kind].append((a, b))
 
-        timed("analysis", lambda: plan.analysis_step(0, ypb, z, c, first=True))
+        timed("analysis", lambda: plan.analysis_step(0, ypb, code, c, first=True))
         for k in range(1, CFG["K"]):
-            timed("synthesis", lambda: plan.synthesis_step(k, z, r, ypb, None, residual=True))
-            timed("analysis", lambda: plan.analysis_step(k, r, z, c))
-        timed("synthesis", lambda: plan.synthesis_step(0, z, r, residual=False))
+            timed("synthesis", lambda: plan.synthesis_step(k, code, r, ypb, None, residual=True))
+            timed("analysis", lambda: plan.analysis_step(k, r, code, c))
+        timed("synthesis", lambda: plan.synthesis_step(0, code, r, residual=False))
         torch.cuda.synchronize()
         tk = {k: [a.elapsed_time(b) for a, b in v] for k, v in acc.items()}
         tot = {k: sum(v) for k, v in tk.items()}

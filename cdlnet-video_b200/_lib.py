@@ -22,7 +22,7 @@ SYMBOLS = [
     "cdl_plan_workspace_bytes", "cdl_plan_precision", "cdl_set_weights", "cdl_reduce_sums",
     "cdl_mean_from_sums", "cdl_center_pad", "cdl_preprocess", "cdl_analysis_step", "cdl_synthesis_step",
     "cdl_forward", "cdl_postprocess", "cdl_denoise", "cdl_plan_host_workspace_bytes", "cdl_denoise_host",
-    "cdl_plan_launch_count",
+    "cdl_plan_launch_count", "cdl_plan_code_bytes", "cdl_code_export", "cdl_code_import",
 ]
 
 
@@ -95,7 +95,7 @@ def load():
         lib.cdl_plan_destroy.argtypes = [vp]
         lib.cdl_plan_layout.restype = i32
         lib.cdl_plan_layout.argtypes = [vp, P(CdlLayout)]
-        for name in ("cdl_plan_workspace_bytes", "cdl_plan_host_workspace_bytes"):
+        for name in ("cdl_plan_workspace_bytes", "cdl_plan_host_workspace_bytes", "cdl_plan_code_bytes"):
             getattr(lib, name).restype = i32
             getattr(lib, name).argtypes = [vp, P(ctypes.c_size_t)]
         lib.cdl_plan_precision.restype = i32
@@ -118,6 +118,9 @@ def load():
         lib.cdl_synthesis_step.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.cdl_forward.restype = i32
         lib.cdl_forward.argtypes = [vp] * 8
+        for name in ("cdl_code_export", "cdl_code_import"):
+            getattr(lib, name).restype = i32
+            getattr(lib, name).argtypes = [vp] * 4
         lib.cdl_postprocess.restype = i32
         lib.cdl_postprocess.argtypes = [vp] * 5
         lib.cdl_denoise.restype = i32

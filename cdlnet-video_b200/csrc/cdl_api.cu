@@ -24,7 +24,7 @@ typedef void (*ana_fn_t)(const AnaParams);
 typedef void (*syn_fn_t)(const SynParams);
 
 struct Offsets {   // byte offsets into the caller's workspace
-  size_t rbuf, partial, sums, yp, mask_p, mean, xphat, end;
+  size_t rbuf, partial, sums, yp, mask_p, mean, xphat, code, end;
   size_t h_y, h_mask, h_c, h_xhat, h_z, h_end;
 };
 
@@ -87,6 +87,7 @@ struct cdl_plan {
   size_t wAtc_layer, wBtc_layer;
   int sm_count;
   bool have_weights;
+  size_t code_bytes;   // bytes of the sparse code in the plan's internal layout
   Offsets off;
   uint64_t launches;
 };
@@ -347,6 +348,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     return CDL_CUDA_ERROR_BASE + (int)e;
   }
 
+  p->code_bytes = (p->tc_ana ? (size_t)g.N * g.coarse_vol() * tc::kNA : (size_t)g.N * g.M * g.coarse_vol()) * sizeof(float);
   // ---- workspace layout ----
   {
     Offsets& o = p->off;
@@ -361,6 +363,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     o.mask_p = cur; cur = align_up(cur + (d->has_mask ? fine_bytes : 0), 256);
     o.mean = cur; cur = align_up(cur + (size_t)g.N * sizeof(float), 256);
     o.xphat = cur; cur = align_up(cur + fine_bytes, 256);
+    o.code = cur; cur = align_up(cur + p->code_bytes, 256);
     o.end = cur;
     o.h_y = cur; cur = align_up(cur + in_bytes, 256);
     o.h_mask = cur; cur = align_up(cur + (d->has_mask ? in_bytes : 0), 256);
@@ -399,6 +402,39 @@ extern "C" int cdl_plan_host_workspace_bytes(const cdl_plan_t* p, size_t* out) {
   return CDL_OK;
 }
 extern "C" int cdl_plan_precision(const cdl_plan_t* p) { return p ? p->precision_eff : CDL_ERR_NULL; }
+extern "C" int cdl_plan_code_bytes(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->code_bytes;
+  return CDL_OK;
+}
+// internal code layout -> (N,M,coarse) as the reference returns z
+extern "C" int cdl_code_export(cdl_plan_t* p, const float* code, float* z, void* stream_) {
+  if (!p || !code || !z) return CDL_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!p->tc_ana) {
+    if (code != z) CDL_CUDA(cudaMemcpyAsync(z, code, p->code_bytes, cudaMemcpyDeviceToDevice, st));
+    return CDL_OK;
+  }
+  const long long Q = p->g.coarse_vol();
+  dim3 grid((unsigned)((Q + 31) / 32), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
+  tc::k_code_export<<<grid, 256, 0, st>>>(code, z, Q, p->g.M);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+// (N,M,coarse) -> internal code layout
+extern "C" int cdl_code_import(cdl_plan_t* p, const float* z, float* code, void* stream_) {
+  if (!p || !code || !z) return CDL_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!p->tc_ana) {
+    if (code != z) CDL_CUDA(cudaMemcpyAsync(code, z, p->code_bytes, cudaMemcpyDeviceToDevice, st));
+    return CDL_OK;
+  }
+  const long long Q = p->g.coarse_vol();
+  dim3 grid((unsigned)((Q + 31) / 32), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
+  tc::k_code_import<<<grid, 256, 0, st>>>(z, code, Q, p->g.M);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
 extern "C" int cdl_plan_launch_count(const cdl_plan_t* p, uint64_t* out) {
   if (!p || !out) return CDL_ERR_NULL;
   *out = p->launches;
@@ -603,12 +639,15 @@ extern "C" int cdl_forward(cdl_plan_t* p, const float* yp, const float* mask_p, 
   if (!p || !yp || !z || !xphat) return CDL_ERR_NULL;
   if (!ws) return CDL_ERR_WORKSPACE;
   float* rbuf = reinterpret_cast<float*>((char*)ws + p->off.rbuf);
-  int rc = cdl_analysis_step(p, 0, 1, yp, c, z, ws, stream_);                      // model/net.py:85,200
+  // the tensor-core kernels keep the code channels-last in the workspace; the fp32 kernels work in place on z
+  float* code = p->tc_ana ? reinterpret_cast<float*>((char*)ws + p->off.code) : z;
+  int rc = cdl_analysis_step(p, 0, 1, yp, c, code, ws, stream_);                   // model/net.py:85,200
   for (int k = 1; k < p->g.K && !rc; ++k) {                                        // model/net.py:86-87,204-205
-    rc = cdl_synthesis_step(p, k, 1, z, yp, mask_p, rbuf, ws, stream_);
-    if (!rc) rc = cdl_analysis_step(p, k, 0, rbuf, c, z, ws, stream_);
+    rc = cdl_synthesis_step(p, k, 1, code, yp, mask_p, rbuf, ws, stream_);
+    if (!rc) rc = cdl_analysis_step(p, k, 0, rbuf, c, code, ws, stream_);
   }
-  if (!rc) rc = cdl_synthesis_step(p, 0, 0, z, nullptr, nullptr, xphat, ws, stream_);   // D = B[0], model/net.py:90,210
+  if (!rc) rc = cdl_synthesis_step(p, 0, 0, code, nullptr, nullptr, xphat, ws, stream_);   // D = B[0], model/net.py:90,210
+  if (!rc) rc = cdl_code_export(p, code, z, stream_);
   return rc;
 }
 

@@ -43,7 +43,7 @@ constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 64;   // TMEM columns: D0 | D
 struct AnaTcParams {
   Geo g;
   const float* rin;     // (N,1,Fd,Fh,Fw) residual (or yp for iteration 0)
-  float* z;             // (N,M,Qd,Qh,Qw) in place
+  float* z;             // internal code layout: channels-last (N,Qd,Qh,Qw,176), updated in place
   const float* wpack;   // this layer: [2 ranks][43 k-steps][11 groups][2][8][4] tf32-rounded filters
   const float* t0;      // [M]
   const float* t1;      // [M]
@@ -158,13 +158,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
             const int row = ch * kChunkRows + rr, td = row / kP, th = row % kP;
             const float2* src = reinterpret_cast<const float2*>(rs + (td * kRH + th) * kRW);
             float2 a = src[0], b = src[1], c = src[2], d = src[3];      // fine w = 2q-4 .. 2q+3 ; taps use 2q-3 .. 2q+3
-            v[rr * 7 + 0] = __float_as_uint(to_tf32_rna(a.y));
-            v[rr * 7 + 1] = __float_as_uint(to_tf32_rna(b.x));
-            v[rr * 7 + 2] = __float_as_uint(to_tf32_rna(b.y));
-            v[rr * 7 + 3] = __float_as_uint(to_tf32_rna(c.x));
-            v[rr * 7 + 4] = __float_as_uint(to_tf32_rna(c.y));
-            v[rr * 7 + 5] = __float_as_uint(to_tf32_rna(d.x));
-            v[rr * 7 + 6] = __float_as_uint(to_tf32_rna(d.y));
+            v[rr * 7 + 0] = tf32_rna_bits(a.y);
+            v[rr * 7 + 1] = tf32_rna_bits(b.x);
+            v[rr * 7 + 2] = tf32_rna_bits(b.y);
+            v[rr * 7 + 3] = tf32_rna_bits(c.x);
+            v[rr * 7 + 4] = tf32_rna_bits(c.y);
+            v[rr * 7 + 5] = tf32_rna_bits(d.x);
+            v[rr * 7 + 6] = tf32_rna_bits(d.y);
           }
           tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&v[0]));
           tmem_st16(acol + 32, *reinterpret_cast<const uint32_t(*)[16]>(&v[32]));
@@ -173,10 +173,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
           uint32_t v[8];
           const float2* src = reinterpret_cast<const float2*>(rs + (6 * kRH + 6) * kRW);
           float2 a = src[0], b = src[1], c = src[2], d = src[3];
-          v[0] = __float_as_uint(to_tf32_rna(a.y)); v[1] = __float_as_uint(to_tf32_rna(b.x));
-          v[2] = __float_as_uint(to_tf32_rna(b.y)); v[3] = __float_as_uint(to_tf32_rna(c.x));
-          v[4] = __float_as_uint(to_tf32_rna(c.y)); v[5] = __float_as_uint(to_tf32_rna(d.x));
-          v[6] = __float_as_uint(to_tf32_rna(d.y)); v[7] = 0u;
+          v[0] = tf32_rna_bits(a.y); v[1] = tf32_rna_bits(b.x);
+          v[2] = tf32_rna_bits(b.y); v[3] = tf32_rna_bits(c.x);
+          v[4] = tf32_rna_bits(c.y); v[5] = tf32_rna_bits(d.x);
+          v[6] = tf32_rna_bits(d.y); v[7] = 0u;
           tmem_st8(acol, v);
         }
         CDL_TW(tw2, tmem_wait_st());
@@ -189,8 +189,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
     const int quad = warp & 3, half = (warp - 4) >> 2;
     const int m0 = half * kNAH;
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
-    const size_t mstride = (size_t)g.coarse_vol();
-    const int mcount = min(kNAH, max(0, g.M - m0));             // real subbands in this warp's half
     const uint32_t usign = p.first ? 0x80000000u : 0u;          // iteration 0: z_in = 0 and v = +u  (0 - (-u))
     float* sTau = sT;                                           // tau[m] of the sample the current tile belongs to
     int n_tau = -1;
@@ -207,57 +205,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         n_tau = n;
       }
       const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
-      const bool valid = qh < g.Qh && qw < g.Qw;
-      const int cnt = valid ? mcount : 0;                       // subbands this thread reads / writes
-      const int cnt_ld = p.first ? 0 : cnt;
-      float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
-      // pull the next tile's z rows towards L2 (676 lines of 128 B per CTA tile, spread over the 256 epilogue threads)
-      if (!p.first && tile + npairs < p.ntiles) {
+      const int valid = qh < g.Qh && qw < g.Qw;
+      const int ld_ok = valid && !p.first;
+      // this site's 88 subbands are contiguous (channels-last): 11 LDG.256 in, 11 STG.256 out
+      float* zs = p.z + ((((size_t)n * g.Qd + qd) * g.Qh + qh) * g.Qw + qw) * kNA + m0;
+      if (!p.first && tile + npairs < p.ntiles) {               // pull the next tile's rows towards L2 (352 B per thread)
         int n2, qd2, qh02, qw02;
         ana_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + quad;
-        if (qh2 < g.Qh) {
-          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02 + (size_t)m0 * mstride;
-          for (int m = lane; m < mcount; m += 32) prefetch_l2(z2 + m * mstride);
+        const int qh2 = qh02 + rank * kTH + quad, qw2 = qw02 + lane;
+        if (qh2 < g.Qh && qw2 < g.Qw) {
+          const float* z2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kNA + m0;
+          prefetch_l2(z2); prefetch_l2(z2 + 32); prefetch_l2(z2 + 64);
         }
       }
-      const long long msb = (long long)mstride * 4;              // byte stride between subbands
       float zc[16];
-      {
-        const char* a = reinterpret_cast<const char*>(zq);
-#pragma unroll
-        for (int i = 0; i < 16; ++i, a += msb) zc[i] = ldg_f32_pred(a, i < cnt_ld);   // batch 0, before the accumulator is ready
-      }
+      ldg256_pred(zs, *reinterpret_cast<float(*)[8]>(&zc[0]), ld_ok);          // batch 0 requested before the accumulator is ready
+      ldg256_pred(zs + 8, *reinterpret_cast<float(*)[8]>(&zc[8]), ld_ok);
       CDL_TW(tw0, mbar_wait(&dfull[ds], (it >> 1) & 1));
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
-      char* zb = reinterpret_cast<char*>(zq);
 #pragma unroll 1
-      for (int b = 0; b < 5; ++b, zb += 16 * msb) {
+      for (int b = 0; b < 5; ++b) {
         uint32_t u[16];
         tmem_ld16(dcol + b * 16, u);
         float zn[16];
-        {
-          const char* a = zb + 16 * msb;
-          const int c2 = cnt_ld - (b + 1) * 16;
-#pragma unroll
-          for (int i = 0; i < 16; ++i, a += msb) zn[i] = ldg_f32_pred(a, i < c2);     // next batch in flight
-        }
+        ldg256_pred(zs + (b + 1) * 16, *reinterpret_cast<float(*)[8]>(&zn[0]), ld_ok);      // next batch in flight
+        if (b < 4) ldg256_pred(zs + (b + 1) * 16 + 8, *reinterpret_cast<float(*)[8]>(&zn[8]), ld_ok);
         tmem_wait_ld();
-        const int c1 = cnt - b * 16;
         const float4* tq = reinterpret_cast<const float4*>(sTau + m0 + b * 16);
-        char* a = zb;
+        float o[16];
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const float4 t4 = tq[i4];
           const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j, a += msb) {
+          for (int j = 0; j < 4; ++j) {
             const int i = i4 * 4 + j;
-            const float v = __fsub_rn(zc[i], __uint_as_float(u[i] ^ usign));
-            stg_f32_pred(a, soft_threshold(v, tt[j]), i < c1);
+            o[i] = soft_threshold(__fsub_rn(zc[i], __uint_as_float(u[i] ^ usign)), tt[j]);
           }
         }
+        stg256_pred(zs + b * 16, *reinterpret_cast<const float(*)[8]>(&o[0]), valid);
+        stg256_pred(zs + b * 16 + 8, *reinterpret_cast<const float(*)[8]>(&o[8]), valid);
 #pragma unroll
         for (int i = 0; i < 16; ++i) zc[i] = zn[i];
       }
@@ -268,13 +256,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         tc_fence_before();                         // accumulator fully read: hand the TMEM slot back to the MMA warp
         __syncwarp();
         if (lane == 0) { if (rank == 0) mbar_arrive(&dempty[ds]); else mbar_arrive_cluster(&dempty[ds], 0); }
-        const int c1 = cnt - 80;
-        char* a = zb;
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i, a += msb) {
-          const float v = __fsub_rn(zc[i], __uint_as_float(u[i] ^ usign));
-          stg_f32_pred(a, soft_threshold(v, sTau[m0 + 80 + i]), i < c1);
-        }
+        for (int i = 0; i < 8; ++i) o[i] = soft_threshold(__fsub_rn(zc[i], __uint_as_float(u[i] ^ usign)), sTau[m0 + 80 + i]);
+        stg256_pred(zs + 80, o, valid);
       }
     }
   } else {

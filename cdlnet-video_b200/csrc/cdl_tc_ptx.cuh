@@ -194,6 +194,19 @@ __device__ __forceinline__ float ldg_f32_pred(const char* addr, int ok) {
 __device__ __forceinline__ void stg_f32_pred(char* addr, float v, int ok) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(ok) : "memory");
 }
+// 256-bit (8 x f32) predicated streaming load / store, 32-byte aligned (sm_100 LDG.256 / STG.256)
+__device__ __forceinline__ void ldg256_pred(const float* p, float (&v)[8], int ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t"
+               "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0; mov.b32 %4, 0; mov.b32 %5, 0; mov.b32 %6, 0; mov.b32 %7, 0;\n\t"
+               "@p ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p), "r"(ok));
+}
+__device__ __forceinline__ void stg256_pred(float* p, const float (&v)[8], int ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t@p st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};\n\t}"
+               ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p), "r"(ok) : "memory");
+}
+// tf32 round-to-nearest (ties away) as two integer ops; inf/nan are not special-cased (z and r are finite)
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ float to_tf32_rna(float x) {   // round-to-nearest (ties away) to 10-bit mantissa
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

@@ -4,20 +4,24 @@
 //
 // `out` is pre-initialised by the caller with -yp (so that it ends up holding the residual B z - yp) or
 // with 0 (final D z).  Formulation: GEMM + col2im,
-//     Pq[q, t] = sum_m z[m, q] * W[m, t]        M_gemm = 256 coarse sites / CTA pair, K = 176, N = 352
+//     Pq[q, t] = sum_m z[q, m] * W[m, t]        M_gemm = 256 coarse sites / CTA pair, K = 176, N = 2 x 176
 //     out[2q - 3 + t] += Pq[q, t]               (overlap-add of each site's 7x7x7 patch)
 //
 //   * cta_group::2, filters resident: each CTA keeps half of the bank (176 taps x 176 subbands, 124 KB).
-//   * A operand = z^T tile: producer threads (one per coarse site = TMEM lane) read z[m, q] straight from
-//     global memory (coalesced over the 32 sites of a warp), round to tf32 (RNE) and tcgen05.st it into
-//     TMEM; two A buffers (2 x 176 columns) so loads of tile i+1 overlap the MMAs of tile i.
-//   * N is processed in 6 chunks (5 x 64 + 32 taps); the accumulator is a 2-slot ring of 64 TMEM columns,
-//     so the col2im epilogue of chunk c overlaps the MMAs of chunk c+1.
+//   * Every tcgen05.mma costs >= ~80 cycles whatever its N (measured, profiles/), so the taps are processed in
+//     two passes of N = 176 (25 + 24 rows of 7 taps): 44 MMAs of 88 cycles per tile instead of 132 short ones.
+//     The two accumulators (2 x 176 TMEM columns) double-buffer each other: the col2im of pass p overlaps the
+//     MMAs of the next pass.
+//   * A operand = the code tile: z is kept channels-last (N,Qd,Qh,Qw,176), so a producer thread (one per coarse
+//     site = TMEM lane) reads its subbands with 256-bit loads, rounds to tf32 (RNE - the tensor core truncates)
+//     and tcgen05.st's them into a 2-slot ring of 64 TMEM columns (3 K-chunks per pass; pass 1 re-reads the
+//     tile from L1/L2).
 //   * col2im: taps are ordered (th, td, tw).  A thread first combines its 7 tw-values with its w-neighbours
 //     by warp shuffles (-> the 2 fine voxels of its own cell, plus 5 spill voxels per warp), then adds a
 //     float2 to the CTA's fine tile in shared memory.  Warps (= h-rows of the tile) proceed in lock step
 //     over th (named barrier between th groups), so no two warps ever touch the same row: no shared-memory
-//     atomics.  The finished 7 x 13 x 69 footprint is added to `out` with red.global.add (tiles overlap).
+//     atomics.  The finished 7 x 13 x 69 footprint is handed to the producer warps, which add it to `out`
+//     with red.global.add.v4.f32 (tiles overlap) while the col2im warps start the next tile.
 #pragma once
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
@@ -26,49 +30,44 @@
 namespace cdl {
 namespace tc {
 
-constexpr int kKB = 176;                  // GEMM K of the synthesis (subbands, padded)
+constexpr int kKB = 176;                  // GEMM K of the synthesis (subbands, padded) = channels of the code layout
 constexpr int kKBSteps = kKB / 8;         // 22
-constexpr int kNB = 352;                  // GEMM N (343 taps padded)
-constexpr int kNChunks = 6;               // 5 x 64 + 32
-constexpr int kColA0 = 0, kColDB = 2 * kKB, kDSlot = 64;   // TMEM: A0 | A1 | D0 | D1  (480 of 512)
-constexpr int kXD = 7, kXH = 13, kXW = 72;                 // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
+constexpr int kNBP = 176;                 // GEMM N per pass
+constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in pass 0 (pass 1: 24)
+constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 64;   // TMEM: D0 | D1 | A0 | A1  (480 of 512)
+constexpr int kXD = 7, kXH = 13, kXW = 72;                   // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
 constexpr int kXTile = kXD * kXH * kXW;
 
 struct SynTcParams {
   Geo g;
-  const float* z;       // (N,M,Qd,Qh,Qw)
+  const float* z;       // channels-last code (N,Qd,Qh,Qw,176)
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
-  const float* wpack;   // this layer: [2 ranks][chunk][22 k-steps][rows/8][2][8][4]
+  const float* wpack;   // this layer: [2 ranks][2 passes][22 k-steps][11 groups][2][8][4]
   int tiles_w, tiles_h, ntiles;
   long long* dbg;
 };
 
-__host__ __device__ constexpr int syn_chunk_rows(int nc) { return nc < 5 ? 32 : 16; }          // B rows per CTA in chunk nc
-constexpr int kRowsPerChunk = 9;                                                                // (th,td) rows of 7 taps per accumulator chunk
-__host__ __device__ constexpr int syn_chunk_nrows(int nc) { return nc < 5 ? 9 : 4; }
-__host__ __device__ constexpr int syn_chunk_off(int nc) { return nc * (kKBSteps * 32 * 8); }   // float offset of chunk nc
-constexpr size_t kSynSmemB = (size_t)(5 * 32 + 16) * kKB * sizeof(float);                      // 123904
-constexpr size_t kSynSmemX = 2 * (size_t)kXTile * sizeof(float);                               // two footprint tiles, 52416
+constexpr size_t kSynSmemB = (size_t)2 * kKBSteps * (kNBP / 2) * 8 * sizeof(float);             // 123904
+constexpr size_t kSynSmemX = 2 * (size_t)kXTile * sizeof(float);                                // two footprint tiles, 52416
 constexpr size_t kSynSmemBytes = kSynSmemB + kSynSmemX + 256;
 
-// filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[n = t' = (th,td,tw), k = m], per-rank UMMA layout, tf32 RNE
+// filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[pass][n = 7*row + tw, k = m], per-rank UMMA layout, tf32 RNE.
+// Pass 0 holds rows 0..24, pass 1 rows 25..48 of the (th,td) row list (th-major); unused columns are zero.
 __global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restrict__ out, int M) {
-  const int per_rank = (5 * 32 + 16) * kKB;
+  const int per_rank = 2 * kKBSteps * (kNBP / 2) * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += gridDim.x * blockDim.x) {
     const int rank = i / per_rank;
     int rem = i % per_rank;
-    int nc = rem / (kKBSteps * 32 * 8);
-    if (nc > 5) nc = 5;
-    rem -= syn_chunk_off(nc);
-    const int rows = syn_chunk_rows(nc);
-    const int ks = rem / (rows * 8);
-    rem %= rows * 8;
+    const int pass = rem / (kKBSteps * (kNBP / 2) * 8);
+    rem %= kKBSteps * (kNBP / 2) * 8;
+    const int ks = rem / ((kNBP / 2) * 8);
+    rem %= (kNBP / 2) * 8;
     const int grp = rem / 64, kc = (rem / 32) % 2, r8 = (rem / 4) % 8, e = rem % 4;
-    const int j = rank * rows + grp * 8 + r8;                  // column inside accumulator chunk nc
+    const int j = rank * (kNBP / 2) + grp * 8 + r8;            // column inside the pass accumulator
     const int m = ks * 8 + kc * 4 + e;
-    const int row = nc * kRowsPerChunk + j / 7, tw = j % 7;    // (th,td) row index, th-major
+    const int row = pass * kRowsP0 + j / 7, tw = j % 7;
     float v = 0.0f;
-    if (j < 7 * syn_chunk_nrows(nc) && row < 49 && m < M) {
+    if (j < 7 * (pass == 0 ? kRowsP0 : 49 - kRowsP0) && m < M) {
       const int th = row / 7, td = row % 7;
       v = w[(size_t)m * kTaps + (td * 7 + th) * 7 + tw];
     }
@@ -142,7 +141,7 @@ __device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs,
   }
 }
 
-// rows [R, REND) of the chunk that starts at row RC0, split at th-group boundaries; warps run the th groups in lock
+// rows [R, REND) whose first row RC0 sits at u[0], split at th-group boundaries; warps run the th groups in lock
 // step (named barrier 2) so that no two warps ever touch the same shared-memory row at the same time
 template <int R, int REND, int RC0, int COLS>
 __device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, int hrow, int lane, const EdgeMasks& em) {
@@ -154,27 +153,41 @@ __device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, 
   }
 }
 
-template <int NC>
-__device__ __forceinline__ void syn_epilogue_chunk(uint32_t taddr, float* xs, int hrow, int lane, const EdgeMasks& em,
-                                                   uint64_t* dempty_slot, uint64_t* dfull_slot, uint32_t parity, long long& tw, uint32_t rank) {
-  using namespace ptx;
-  constexpr int COLS = NC < 5 ? 64 : 32;
-  CDL_TW(tw, mbar_wait(dfull_slot, parity));
-  tc_fence_after();
-  uint32_t u[COLS];
-  if constexpr (COLS == 64) tmem_ld64(taddr, u); else tmem_ld32(taddr, u);
-  tmem_wait_ld();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) { if (rank == 0) mbar_arrive(dempty_slot); else mbar_arrive_cluster(dempty_slot, 0); }   // accumulator slot is free again
-  rows_walk<NC * kRowsPerChunk, NC * kRowsPerChunk + syn_chunk_nrows(NC), NC * kRowsPerChunk, COLS>(u, xs, hrow, lane, em);
-}
-
 __device__ __forceinline__ void syn_tile_coords(const SynTcParams& p, int tile, int& n, int& qd, int& qh0, int& qw0) {
   int tw = tile % p.tiles_w; tile /= p.tiles_w;
   int th = tile % p.tiles_h; tile /= p.tiles_h;
   qd = tile % p.g.Qd; n = tile / p.g.Qd;
   qh0 = th * 2 * kTH; qw0 = tw * kTW;
+}
+
+// one accumulator pass (176 columns = rows [RFIRST, RLAST) of 7 taps) drained in three 64-column loads of 9/9/rest rows
+template <int RFIRST, int RLAST>
+__device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int hrow, int lane, const EdgeMasks& em,
+                                                  uint64_t* dempty_p, uint64_t* dfull_p, uint32_t parity, long long& tw, uint32_t rank) {
+  using namespace ptx;
+  CDL_TW(tw, mbar_wait(dfull_p, parity));
+  tc_fence_after();
+  {
+    uint32_t u[64];
+    tmem_ld64(dcol, u);
+    tmem_wait_ld();
+    rows_walk<RFIRST, RFIRST + 9, RFIRST, 64>(u, xs, hrow, lane, em);
+  }
+  {
+    uint32_t u[64];
+    tmem_ld64(dcol + 63, u);
+    tmem_wait_ld();
+    rows_walk<RFIRST + 9, RFIRST + 18, RFIRST + 9, 64>(u, xs, hrow, lane, em);
+  }
+  {
+    uint32_t u[64];
+    tmem_ld64(dcol + 126, u);                      // rows RFIRST+18 .. RLAST-1 (49 or 42 columns); the rest is ignored
+    tmem_wait_ld();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) { if (rank == 0) mbar_arrive(dempty_p); else mbar_arrive_cluster(dempty_p, 0); }   // accumulator free again
+    rows_walk<RFIRST + 18, RLAST, RFIRST + 18, 64>(u, xs, hrow, lane, em);
+  }
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_synthesis(const SynTcParams p) {
@@ -186,7 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   uint64_t* wbar = bars + 0;
   uint64_t* afull = bars + 1;    // [2] (leader) producers of both CTAs -> MMA
   uint64_t* aempty = bars + 3;   // [2] MMA commit (multicast) -> producers
-  uint64_t* dfull = bars + 5;    // [2] MMA commit (multicast) -> epilogue
+  uint64_t* dfull = bars + 5;    // [2] MMA commit (multicast) -> epilogue   (index = pass)
   uint64_t* dempty = bars + 7;   // [2] (leader) epilogue warps of both CTAs -> MMA
   uint64_t* wready = bars + 9;   //     (leader) the peer CTA's filters have landed
   uint64_t* xfull = bars + 10;   // [2] epilogue -> producers: footprint tile complete, flush it
@@ -220,17 +233,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   cluster_sync_all();          // barriers initialised, TMEM allocated (filters may still be in flight)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
-  const size_t mstride = (size_t)g.coarse_vol();
 
   if (warp < 8) {
-    // ============================== producers: z[m, q] -> tf32 -> TMEM A ==============================
-    // warp = 4*half + quad: TMEM lanes of tile row `quad`, subbands [88*half, 88*half+88)
+    // ============================== producers: code tile -> tf32 -> TMEM A ring; footprint flush ==============================
+    // warp = 4*half + quad: TMEM lanes of tile row `quad`; `half` selects which half of every K-chunk this warp converts
     const int quad = warp & 3, half = warp >> 2;
-    const int m0 = half * (kKB / 2);
-    const int mcount = min(kKB / 2, max(0, g.M - m0));
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
-    // out[fine] += footprint of tile `t` (the j-th tile of this CTA), then clear the buffer for tile j+2.
-    // Done by the 256 producer threads so the col2im warps can move straight on to the next tile.
+    // out[fine] += footprint of tile `t` (the j-th tile of this CTA), then clear the buffer for tile j+2
     auto flush_tile = [&](int t, int j) {
       const int xb = j & 1;
       CDL_TW(tw1, mbar_wait(&xfull[xb], (j >> 1) & 1));
@@ -255,53 +264,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       if (lane == 0) mbar_arrive(&xfree[xb]);
     };
     int it = 0;
+    uint32_t gch = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
-      const uint32_t ab = it & 1;
       int n, qd, qh0, qw0;
       syn_tile_coords(p, tile, n, qd, qh0, qw0);
       const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
-      const bool valid = qh < g.Qh && qw < g.Qw;
-      const float* zq = p.z + (((size_t)n * g.M * g.Qd + qd) * g.Qh + qh) * g.Qw + qw + (size_t)m0 * mstride;
-      // pull the next tile's rows of z towards L2 while this one is converted
-      if (tile + npairs < p.ntiles) {
+      const int valid = qh < g.Qh && qw < g.Qw;
+      const float* zs = p.z + ((((size_t)n * g.Qd + qd) * g.Qh + qh) * g.Qw + qw) * kKB;
+      if (tile + npairs < p.ntiles) {                            // pull the next tile's code towards L2 (352 B per thread)
         int n2, qd2, qh02, qw02;
         syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + quad;
-        if (qh2 < g.Qh) {
-          const float* z2 = p.z + (((size_t)n2 * g.M * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02;
-          for (int m = lane; m < mcount; m += 32) prefetch_l2(z2 + (size_t)(m0 + m) * mstride);
+        const int qh2 = qh02 + rank * kTH + quad, qw2 = qw02 + lane;
+        if (qh2 < g.Qh && qw2 < g.Qw) {
+          const float* z2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kKB + half * (kKB / 2);
+          prefetch_l2(z2); prefetch_l2(z2 + 32); prefetch_l2(z2 + 64);
         }
       }
-      const uint32_t acol = lane_addr + kColA0 + ab * kKB + m0;
-      const int cnt = valid ? mcount : 0;
-      const long long msb = (long long)mstride * 4;
-      const char* a = reinterpret_cast<const char*>(zq);
-      uint32_t v[32];
+#pragma unroll 1
+      for (int pc = 0; pc < 6; ++pc, ++gch) {                    // 2 passes x 3 K-chunks (64, 64, 48 subbands)
+        const int c = pc % 3;
+        const uint32_t slot = gch & 1;
+        const uint32_t acol = lane_addr + kColAB + slot * kASlotB;
+        if (c < 2) {
+          float v[32];
+          const float* src = zs + c * 64 + half * 32;
 #pragma unroll
-      for (int i = 0; i < 32; ++i, a += msb) v[i] = __float_as_uint(ldg_f32_pred(a, i < cnt));
-      CDL_TW(tw0, mbar_wait(&aempty[ab], ((it >> 1) & 1) ^ 1));     // first batch is in flight while the MMAs still read this buffer
-      tc_fence_after();
+          for (int i = 0; i < 4; ++i) ldg256_pred(src + 8 * i, *reinterpret_cast<float(*)[8]>(&v[8 * i]), valid);
+          CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));     // loads are in flight while the MMAs still read this slot
+          tc_fence_after();
+          uint32_t b[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
-      tmem_st32(acol, v);
+          for (int i = 0; i < 32; ++i) b[i] = tf32_rna_bits(v[i]);
+          tmem_st32(acol + half * 32, b);
+        } else {
+          float v[24];
+          const float* src = zs + 128 + half * 24;
 #pragma unroll
-      for (int i = 0; i < 32; ++i, a += msb) v[i] = __float_as_uint(ldg_f32_pred(a, i + 32 < cnt));
+          for (int i = 0; i < 3; ++i) ldg256_pred(src + 8 * i, *reinterpret_cast<float(*)[8]>(&v[8 * i]), valid);
+          CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));
+          tc_fence_after();
+          uint32_t b[24];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32_rna(__uint_as_float(v[i])));
-      tmem_st32(acol + 32, v);
-      {
-        uint32_t w[24];
-#pragma unroll
-        for (int i = 0; i < 24; ++i, a += msb) w[i] = __float_as_uint(ldg_f32_pred(a, i + 64 < cnt));
-#pragma unroll
-        for (int i = 0; i < 24; ++i) w[i] = __float_as_uint(to_tf32_rna(__uint_as_float(w[i])));
-        tmem_st16(acol + 64, *reinterpret_cast<const uint32_t(*)[16]>(&w[0]));
-        tmem_st8(acol + 80, *reinterpret_cast<const uint32_t(*)[8]>(&w[16]));
+          for (int i = 0; i < 24; ++i) b[i] = tf32_rna_bits(v[i]);
+          tmem_st16(acol + half * 24, *reinterpret_cast<const uint32_t(*)[16]>(&b[0]));
+          tmem_st8(acol + half * 24 + 16, *reinterpret_cast<const uint32_t(*)[8]>(&b[16]));
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); }
       }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (rank == 0) mbar_arrive(&afull[ab]); else mbar_arrive_cluster(&afull[ab], 0); }
       if (it > 0) flush_tile(tile - npairs, it - 1);
     }
     if (it > 0) flush_tile(pair + (it - 1) * npairs, it - 1);      // footprint of the last tile
@@ -309,19 +321,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     // ============================== epilogue: col2im ==============================
     const int ew = warp - 8;
     const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
-    const int et = tid - 256;
     const EdgeMasks em = {lane < 31 ? 1.0f : 0.0f, lane < 30 ? 1.0f : 0.0f, lane > 0 ? 1.0f : 0.0f};
-    uint32_t gch = 0;
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       const int xb = it & 1;
       float* xs = sX + xb * kXTile;
       CDL_TW(tw1, mbar_wait(&xfree[xb], ((it >> 1) & 1) ^ 1));      // footprint buffer flushed + cleared (first two uses pass)
-      // six accumulator chunks (9,9,9,9,9,4 rows of 7 taps), ring of 2 slots
-#define CDL_CHUNK(NC) { const uint32_t s_ = gch & 1; \
-        syn_epilogue_chunk<NC>(lane_addr + kColDB + s_ * kDSlot, xs, ew, lane, em, &dempty[s_], &dfull[s_], (gch >> 1) & 1, tw0, rank); ++gch; }
-      CDL_CHUNK(0) CDL_CHUNK(1) CDL_CHUNK(2) CDL_CHUNK(3) CDL_CHUNK(4) CDL_CHUNK(5)
-#undef CDL_CHUNK
+      syn_epilogue_pass<0, kRowsP0>(lane_addr + kColDB, xs, ew, lane, em, &dempty[0], &dfull[0], it & 1, tw0, rank);
+      syn_epilogue_pass<kRowsP0, 49>(lane_addr + kColDB + kNBP, xs, ew, lane, em, &dempty[1], &dfull[1], it & 1, tw0, rank);
       __syncwarp();
       if (lane == 0) mbar_arrive(&xfull[xb]);      // this warp's rows are in; 4 arrivals -> producers flush the tile
       named_bar_sync(2, 128);                      // th lock step restarts with everyone at group 0
@@ -332,31 +339,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     if (rank == 0 && lane == 0) {
       CDL_TW(tw2, mbar_wait(wbar, 0); mbar_wait_cluster(wready, 0));
       const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
-      const uint32_t idesc64 = make_idesc_tf32(256, 64), idesc32 = make_idesc_tf32(256, 32);
+      constexpr uint32_t kBStep = ((kNBP / 2) * 32) >> 4;           // 16-byte units between k-steps of B (88 rows x 32 B)
+      const uint32_t idesc = make_idesc_tf32(256, kNBP);
       int it = 0;
       uint32_t gch = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
-        const uint32_t ab = it & 1;
-        CDL_TW(tw1, mbar_wait_cluster(&afull[ab], (it >> 1) & 1));
-        tc_fence_after();
-        const uint32_t acol = tbase + kColA0 + ab * kKB;
-        for (int nc = 0; nc < kNChunks; ++nc, ++gch) {
-          const uint32_t s = gch & 1;
-          CDL_TW(tw0, mbar_wait_cluster(&dempty[s], ((gch >> 1) & 1) ^ 1));
+        for (int pass = 0; pass < 2; ++pass) {
+          CDL_TW(tw0, mbar_wait_cluster(&dempty[pass], (it & 1) ^ 1));
           tc_fence_after();
-          const uint32_t dcol = tbase + kColDB + s * kDSlot;
-          if (nc < 5) {
-            const uint64_t bd = bdesc0 + (uint64_t)nc * ((kKBSteps * 32 * 32) >> 4);
+          const uint32_t dcol = tbase + kColDB + pass * kNBP;
+          for (int c = 0; c < 3; ++c, ++gch) {
+            const uint32_t slot = gch & 1;
+            CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gch >> 1) & 1));
+            tc_fence_after();
+            const uint32_t a0 = tbase + kColAB + slot * kASlotB;
+            const uint64_t bd = bdesc0 + (uint64_t)(pass * kKBSteps + c * 8) * kBStep;
+            if (c < 2) {
 #pragma unroll
-            for (int ks = 0; ks < kKBSteps; ++ks) mma_tf32_ts<2>(dcol, acol + ks * 8, bd + (uint64_t)ks * ((32 * 32) >> 4), idesc64, ks > 0);
-          } else {
-            const uint64_t bd = bdesc0 + (uint64_t)5 * ((kKBSteps * 32 * 32) >> 4);
+              for (int j = 0; j < 8; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, (c | j) != 0);
+            } else {
 #pragma unroll
-            for (int ks = 0; ks < kKBSteps; ++ks) mma_tf32_ts<2>(dcol, acol + ks * 8, bd + (uint64_t)ks * ((16 * 32) >> 4), idesc32, ks > 0);
+              for (int j = 0; j < 6; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, 1);
+            }
+            mma_commit<2>(&aempty[slot]);             // A slot reusable once these MMAs have read it
           }
-          mma_commit<2>(&dfull[s]);
+          mma_commit<2>(&dfull[pass]);                // this pass's accumulator is complete -> col2im (both CTAs)
         }
-        mma_commit<2>(&aempty[ab]);               // A buffer reusable once every chunk's MMAs have read it
       }
     }
     __syncwarp();
@@ -368,6 +376,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   tc_fence_before();
   cluster_sync_all();
   if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
+}
+
+// ---- code layout conversion: internal channels-last (N,Q,176) <-> reference (N,M,Q) ----
+// 32 x 32 tile transpose through shared memory; q and m both coalesced on their respective sides
+__global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ zcl, float* __restrict__ z, long long Q, int M) {
+  __shared__ float t[32][33];
+  const long long q0 = (long long)blockIdx.x * 32;
+  const int m0 = blockIdx.y * 32, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const long long q = q0 + r; const int m = m0 + tx;
+    t[r][tx] = (q < Q && m < kKB) ? zcl[((long long)n * Q + q) * kKB + m] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int m = m0 + r; const long long q = q0 + tx;
+    if (m < M && q < Q) z[((long long)n * M + m) * Q + q] = t[tx][r];
+  }
+}
+__global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z, float* __restrict__ zcl, long long Q, int M) {
+  __shared__ float t[32][33];
+  const long long q0 = (long long)blockIdx.x * 32;
+  const int m0 = blockIdx.y * 32, n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int m = m0 + r; const long long q = q0 + tx;
+    t[r][tx] = (m < M && q < Q) ? z[((long long)n * M + m) * Q + q] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const long long q = q0 + r; const int m = m0 + tx;
+    if (q < Q && m < kKB) zcl[((long long)n * Q + q) * kKB + m] = t[tx][r];
+  }
 }
 
 }  // namespace tc

@@ -16,7 +16,7 @@ using namespace cdl::ptx;
 // B packed per K-step j (8 k-values): [j][n/8][k/4][n%8][k%4]  (SBO = 256 B between 8-row groups, LBO = 128 B between k-chunks)
 // For CG == 2 each CTA holds rows [rank*N/2, (rank+1)*N/2) of B, same packing with N/2 rows.
 template <int CG, bool TS>
-__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K) {
+__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K, int rep, long long* cyc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
 
   if (rank == 0 && tid == 0) {
     const uint32_t idesc = make_idesc_tf32(128 * CG, N);
+    const long long t0 = clock64();
+    for (int r = 0; r < rep; ++r)
     for (int j = 0; j < KS; ++j) {
       uint64_t bdesc = make_smem_desc_kmajor_noswz(smem_u32(sB) + j * NL * 32, 128, 256);
       if (TS) mma_tf32_ts<CG>(tbase, tbase + ACOL + j * 8, bdesc, idesc, j > 0);
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
       }
     }
     mma_commit<CG>(&bar);
+    mbar_wait(&bar, 0);
+    if (cyc) cyc[0] = clock64() - t0;
   }
   mbar_wait(&bar, 0);
   tc_fence_after();
@@ -86,11 +90,15 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
 
 int main(int argc, char** argv) {
   int cg = argc > 1 ? atoi(argv[1]) : 1, ts = argc > 2 ? atoi(argv[2]) : 0, N = argc > 3 ? atoi(argv[3]) : 176, KS = argc > 4 ? atoi(argv[4]) : 7;
+  int rep = argc > 5 ? atoi(argv[5]) : 1, probe = argc > 6 ? atoi(argv[6]) : 0;
   const int M = 128 * cg, K = KS * 8;
   std::vector<float> A((size_t)M * K), B((size_t)N * K), Bp((size_t)N * K), D((size_t)M * N, -1.f), R((size_t)M * N);
   uint32_t s = 12345;
   auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (int)((s >> 20) % 9) - 4; };
   for (auto& v : A) v = rnd() / 4.0f;
+  if (probe) for (auto& v : A) v = 1.0f + 0.75f / 2048.0f;      // 1 + 0.75 ulp_tf32/2...: RNE -> 1 + 2^-10, truncation -> 1
+  if (probe) for (auto& v : B) v = 0.0f;
+  if (probe) for (int n = 0; n < N; ++n) B[(size_t)n * K] = 1.0f;   // picks A[m][0]
   for (auto& v : B) v = rnd() / 8.0f;
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
@@ -115,12 +123,16 @@ int main(int argc, char** argv) {
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  void (*fn)(const float*, const float*, float*, int, int) =
+  long long* dcyc; CK(cudaMalloc(&dcyc, 8)); CK(cudaMemset(dcyc, 0, 8));
+  void (*fn)(const float*, const float*, float*, int, int, int, long long*) =
       cg == 1 ? (ts ? k_gemm<1, true> : k_gemm<1, false>) : (ts ? k_gemm<2, true> : k_gemm<2, false>);
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K));
+  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K, rep, dcyc));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  long long hc = 0; CK(cudaMemcpy(&hc, dcyc, 8, cudaMemcpyDeviceToHost));
+  if (rep > 1) printf("timing cg=%d ts=%d N=%d KS=%d rep=%d : %.1f cycles per MMA\n", cg, ts, N, KS, rep, (double)hc / ((double)rep * KS));
+  if (probe) { printf("rounding probe: A = 1 + 0.75*2^-11 (tf32 ulp 2^-10): D[0][0] = %.10f  (1.0 = truncation, 1.0009765625 = round-to-nearest)\n", D[0]); return 0; }
   double maxerr = 0; long bad = 0;
   for (size_t i = 0; i < D.size(); ++i) { double e = fabs((double)D[i] - R[i]); if (e > maxerr) maxerr = e; if (e > 1e-5) ++bad; }
   printf("selftest cg=%d ts=%d M=%d N=%d K=%d : max|err|=%.3e bad=%ld/%zu  %s\n", cg, ts, M, N, K, maxerr, bad, D.size(), bad ? "FAIL" : "PASS");

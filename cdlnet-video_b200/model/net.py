@@ -141,14 +141,14 @@ class _ISTANet(nn.Module):
         plan, y, mask, c = self._prepare(y, sigma, mask)
         with torch.cuda.device(y.device):
             yp, mp, mean = plan.preprocess(y, mask)
-            z = torch.empty(plan.z_shape, dtype=torch.float32, device=y.device)
+            z = plan.new_code()                  # the code stays in the plan's internal layout between steps
             r = torch.empty_like(yp)
             plan.analysis_step(0, yp, z, c, first=True)
-            yield z.clone()
+            yield plan.export_code(z)
             for k in range(1, self.K):
                 plan.synthesis_step(k, z, r, yp, mp, residual=True)
                 plan.analysis_step(k, r, z, c)
-                yield z.clone()
+                yield plan.export_code(z)
             plan.synthesis_step(0, z, r, residual=False)
             yield plan.postprocess(r, mean)
 

@@ -54,6 +54,8 @@ class Plan:
         self.workspace_bytes = n.value
         _lib.check(self.lib.cdl_plan_host_workspace_bytes(handle, ctypes.byref(n)))
         self.host_workspace_bytes = n.value
+        _lib.check(self.lib.cdl_plan_code_bytes(handle, ctypes.byref(n)))
+        self.code_bytes = n.value
         self._ws = None
         self._weights_key = None
         self._keep = None
@@ -129,6 +131,20 @@ class Plan:
                                              _ptr(z_host), _ptr(ws), _stream()), "cdl_denoise_host")
 
     # stepwise API (forward_generator, temporal slabs) ----------------------------------------------
+    # The sparse code lives in the plan's internal layout between steps (see include/cdl_b200.h).
+    def new_code(self):
+        return torch.zeros(self.code_bytes // 4, dtype=torch.float32, device=self.device)
+
+    def export_code(self, code):
+        z = torch.empty(self.z_shape, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.cdl_code_export(self.handle, _ptr(code), _ptr(z), _stream()), "cdl_code_export")
+        return z
+
+    def import_code(self, z):
+        code = self.new_code()
+        _lib.check(self.lib.cdl_code_import(self.handle, _ptr(z.contiguous()), _ptr(code), _stream()), "cdl_code_import")
+        return code
+
     def preprocess(self, y, mask=None):
         yp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device)
         mp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device) if self.has_mask else None

@@ -98,11 +98,18 @@ int cdl_mean_from_sums(cdl_plan_t* plan, const double* sums, float* mean, void* 
 int cdl_center_pad(cdl_plan_t* plan, const float* y, const float* mask, const float* mean, float* yp, float* mask_p, void* stream);
 int cdl_preprocess(cdl_plan_t* plan, const float* y, const float* mask, float* yp, float* mask_p, float* mean, void* workspace, void* stream);
 
-/* One analysis step  z <- ST(z_in -/+ A_k r, t[k,0] + c*t[k,1])   (model/net.py:85,87;200,205).
- * first != 0: z <- ST(A_k r, .) with r = yp (iteration 0, no z_in).  In place on z.  c: N floats or NULL. */
-int cdl_analysis_step(cdl_plan_t* plan, int k, int first, const float* r, const float* c, float* z, void* workspace, void* stream);
+/* The stepwise entry points keep the sparse code in the plan's INTERNAL layout (`code`, cdl_plan_code_bytes bytes):
+ * (N,M,coarse) for the fp32 kernels, channels-last (N,coarse,176) for the tensor-core kernels.  Convert with
+ * cdl_code_export / cdl_code_import; cdl_forward / cdl_denoise always return z as (N,M,coarse).                      */
+int cdl_plan_code_bytes(const cdl_plan_t* plan, size_t* out);
+int cdl_code_export(cdl_plan_t* plan, const float* code, float* z, void* stream);
+int cdl_code_import(cdl_plan_t* plan, const float* z, float* code, void* stream);
+
+/* One analysis step  code <- ST(code -/+ A_k r, t[k,0] + c*t[k,1])   (model/net.py:85,87;200,205).
+ * first != 0: code <- ST(A_k r, .) with r = yp (iteration 0, no input code).  In place.  c: N floats or NULL. */
+int cdl_analysis_step(cdl_plan_t* plan, int k, int first, const float* r, const float* c, float* code, void* workspace, void* stream);
 /* One synthesis step  out <- mask_p * B_k z - yp  (residual != 0) or out <- B_k z (residual == 0). */
-int cdl_synthesis_step(cdl_plan_t* plan, int k, int residual, const float* z, const float* yp, const float* mask_p, float* out, void* workspace, void* stream);
+int cdl_synthesis_step(cdl_plan_t* plan, int k, int residual, const float* code, const float* yp, const float* mask_p, float* out, void* workspace, void* stream);
 
 /* All K iterations + D z:  z (N,M,coarse) and xphat (N,C,fine) out.                              */
 int cdl_forward(cdl_plan_t* plan, const float* yp, const float* mask_p, const float* c, float* z, float* xphat, void* workspace, void* stream);

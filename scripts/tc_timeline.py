@@ -16,7 +16,7 @@ plan.set_weights(A, B, torch.rand(K, 2, M, device=d) * 0.01)
 clean, y = bench.synthetic_clip(torch, clips, 0, d)
 c = torch.full((clips,), 25 / 255.0, device=d)
 yp, _, mean = plan.preprocess(y)
-z = torch.empty(plan.z_shape, device=d)
+z = plan.new_code()
 r = torch.empty_like(yp)
 plan.analysis_step(0, yp, z, c, first=True)
 for k in range(1, 4):

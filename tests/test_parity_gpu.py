@@ -139,14 +139,15 @@ def test_stepwise_api_equals_fused_forward():
     yd = y.to(d)
     xhat, z = plan.denoise(yd, None, c)
     yp, mp, mean = plan.preprocess(yd)
-    z2 = torch.empty_like(z)
+    code = plan.new_code()
     r = torch.empty_like(yp)
-    plan.analysis_step(0, yp, z2, c, first=True)
+    plan.analysis_step(0, yp, code, c, first=True)
     for k in range(1, K):
-        plan.synthesis_step(k, z2, r, yp, None, residual=True)
-        plan.analysis_step(k, r, z2, c)
-    plan.synthesis_step(0, z2, r, residual=False)
+        plan.synthesis_step(k, code, r, yp, None, residual=True)
+        plan.analysis_step(k, r, code, c)
+    plan.synthesis_step(0, code, r, residual=False)
     x2 = plan.postprocess(r, mean)
+    z2 = plan.export_code(code)
     assert torch.equal(z, z2) and torch.equal(xhat, x2)       # deterministic kernels: bitwise equal
 
 
@@ -162,10 +163,11 @@ def test_adjoint_and_linearity_properties_at_scale():
     plan.set_weights([W] * K, [W] * K, t0)
     x = torch.randn(plan.fine_shape, generator=g).to(d)
     zz = torch.randn(plan.z_shape, generator=g).to(d)
-    u = torch.empty(plan.z_shape, device=d)
-    plan.analysis_step(0, x, u, None, first=True)             # t == 0 -> ST is the identity: u = A x
+    ucode = plan.new_code()
+    plan.analysis_step(0, x, ucode, None, first=True)         # t == 0 -> ST is the identity: u = A x
+    u = plan.export_code(ucode)
     bz = torch.empty(plan.fine_shape, device=d)
-    plan.synthesis_step(0, zz, bz, residual=False)
+    plan.synthesis_step(0, plan.import_code(zz), bz, residual=False)
     lhs = (u.double() * zz.double()).sum().item()
     rhs = (x.double() * bz.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)

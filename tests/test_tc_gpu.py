@@ -62,8 +62,9 @@ def test_tf32_cfg2_full_size_parity():
     assert plan.precision == "tf32"
     plan.set_weights(A, B, torch.zeros(K, 2, M, device=d))
     yp, _, _ = plan.preprocess(y)
-    z0 = torch.empty(plan.z_shape, device=d)
+    z0 = plan.new_code()
     plan.analysis_step(0, yp, z0, None, first=True)
+    z0 = plan.export_code(z0)
     q = torch.quantile(z0[0].abs().reshape(M, -1)[:, ::8].float(), 0.85, dim=1)
     t = bench.thresholds_from_quantile(torch, q, u)
     plan.set_weights(A, B, t)
