@@ -209,13 +209,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
       const int ld_ok = valid && !p.first;
       // this site's 88 subbands are contiguous (channels-last): 11 LDG.256 in, 11 STG.256 out
       float* zs = p.z + ((((size_t)n * g.Qd + qd) * g.Qh + qh) * g.Qw + qw) * kNA + m0;
-      if (!p.first && tile + npairs < p.ntiles) {               // pull the next tile's rows towards L2 (352 B per thread)
+      if (!p.first && half == 0 && lane == 0 && tile + npairs < p.ntiles) {   // next tile: this row's 32 sites x 704 B are contiguous
         int n2, qd2, qh02, qw02;
         ana_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + quad, qw2 = qw02 + lane;
-        if (qh2 < g.Qh && qw2 < g.Qw) {
-          const float* z2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kNA + m0;
-          prefetch_l2(z2); prefetch_l2(z2 + 32); prefetch_l2(z2 + 64);
+        const int qh2 = qh02 + rank * kTH + quad;
+        if (qh2 < g.Qh) {
+          const int nq = min(kTW, g.Qw - qw02);
+          bulk_prefetch_l2(p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02) * kNA, (uint32_t)nq * kNA * 4);
         }
       }
       float zc[16];

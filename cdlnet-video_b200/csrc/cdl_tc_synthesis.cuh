@@ -271,41 +271,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
       const int valid = qh < g.Qh && qw < g.Qw;
       const float* zs = p.z + ((((size_t)n * g.Qd + qd) * g.Qh + qh) * g.Qw + qw) * kKB;
-      if (tile + npairs < p.ntiles) {                            // pull the next tile's code towards L2 (352 B per thread)
+      if (half == 0 && lane == 0 && tile + npairs < p.ntiles) {  // next tile: this row's 32 sites x 704 B are contiguous
         int n2, qd2, qh02, qw02;
         syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + quad, qw2 = qw02 + lane;
-        if (qh2 < g.Qh && qw2 < g.Qw) {
-          const float* z2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kKB + half * (kKB / 2);
-          prefetch_l2(z2); prefetch_l2(z2 + 32); prefetch_l2(z2 + 64);
+        const int qh2 = qh02 + rank * kTH + quad;
+        if (qh2 < g.Qh) {
+          const int nq = min(kTW, g.Qw - qw02);
+          bulk_prefetch_l2(p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02) * kKB, (uint32_t)nq * kKB * 4);
         }
       }
+      // software pipeline: the 32 (24) subbands of K-chunk g+1 are requested before chunk g is converted
+      float vn[32];
+      auto request = [&](int pcn) {
+        const int cn = pcn % 3;
+        const float* src = zs + (cn < 2 ? cn * 64 + half * 32 : 128 + half * 24);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ldg256_pred(src + 8 * i, *reinterpret_cast<float(*)[8]>(&vn[8 * i]), valid);
+        ldg256_pred(src + 24, *reinterpret_cast<float(*)[8]>(&vn[24]), valid && cn < 2);
+      };
+      request(0);
 #pragma unroll 1
       for (int pc = 0; pc < 6; ++pc, ++gch) {                    // 2 passes x 3 K-chunks (64, 64, 48 subbands)
         const int c = pc % 3;
         const uint32_t slot = gch & 1;
         const uint32_t acol = lane_addr + kColAB + slot * kASlotB;
+        uint32_t b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) b[i] = tf32_rna_bits(vn[i]);
+        if (pc < 5) request(pc + 1);
+        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));
+        tc_fence_after();
         if (c < 2) {
-          float v[32];
-          const float* src = zs + c * 64 + half * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ldg256_pred(src + 8 * i, *reinterpret_cast<float(*)[8]>(&v[8 * i]), valid);
-          CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));     // loads are in flight while the MMAs still read this slot
-          tc_fence_after();
-          uint32_t b[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) b[i] = tf32_rna_bits(v[i]);
           tmem_st32(acol + half * 32, b);
         } else {
-          float v[24];
-          const float* src = zs + 128 + half * 24;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) ldg256_pred(src + 8 * i, *reinterpret_cast<float(*)[8]>(&v[8 * i]), valid);
-          CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));
-          tc_fence_after();
-          uint32_t b[24];
-#pragma unroll
-          for (int i = 0; i < 24; ++i) b[i] = tf32_rna_bits(v[i]);
           tmem_st16(acol + half * 24, *reinterpret_cast<const uint32_t(*)[16]>(&b[0]));
           tmem_st8(acol + half * 24 + 16, *reinterpret_cast<const uint32_t(*)[8]>(&b[16]));
         }
