@@ -218,49 +218,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
           bulk_prefetch_l2(p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02) * kNA, (uint32_t)nq * kNA * 4);
         }
       }
-      float zc[16];
-      ldg256_pred(zs, *reinterpret_cast<float(*)[8]>(&zc[0]), ld_ok);          // batch 0 requested before the accumulator is ready
-      ldg256_pred(zs + 8, *reinterpret_cast<float(*)[8]>(&zc[8]), ld_ok);
+      // all 88 code values of this site are requested BEFORE waiting for the accumulator (11 x LDG.256 in flight per
+      // thread, 90 KB per SM): the DRAM latency hides behind the MMAs of this tile; results overwrite the registers
+      float zr[kNAH];
+#pragma unroll
+      for (int b = 0; b < kNAH / 8; ++b) ldg256_pred(zs + 8 * b, *reinterpret_cast<float(*)[8]>(&zr[8 * b]), ld_ok);
       CDL_TW(tw0, mbar_wait(&dfull[ds], (it >> 1) & 1));
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
-#pragma unroll 1
-      for (int b = 0; b < 5; ++b) {
-        uint32_t u[16];
-        tmem_ld16(dcol + b * 16, u);
-        float zn[16];
-        ldg256_pred(zs + (b + 1) * 16, *reinterpret_cast<float(*)[8]>(&zn[0]), ld_ok);      // next batch in flight
-        if (b < 4) ldg256_pred(zs + (b + 1) * 16 + 8, *reinterpret_cast<float(*)[8]>(&zn[8]), ld_ok);
+      uint32_t ua[8], ub[8];
+      tmem_ld8(dcol, ua);
+#pragma unroll
+      for (int b = 0; b < kNAH / 8; ++b) {
+        uint32_t (&u)[8] = (b & 1) ? ub : ua;
+        uint32_t (&un)[8] = (b & 1) ? ua : ub;
         tmem_wait_ld();
-        const float4* tq = reinterpret_cast<const float4*>(sTau + m0 + b * 16);
-        float o[16];
+        if (b + 1 < kNAH / 8) tmem_ld8(dcol + 8 * (b + 1), un);            // next 8 accumulator columns in flight
+        const float4 t0 = *reinterpret_cast<const float4*>(sTau + m0 + 8 * b);
+        const float4 t1 = *reinterpret_cast<const float4*>(sTau + m0 + 8 * b + 4);
+        const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 t4 = tq[i4];
-          const float tt[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = i4 * 4 + j;
-            o[i] = soft_threshold(__fsub_rn(zc[i], __uint_as_float(u[i] ^ usign)), tt[j]);
-          }
-        }
-        stg256_pred(zs + b * 16, *reinterpret_cast<const float(*)[8]>(&o[0]), valid);
-        stg256_pred(zs + b * 16 + 8, *reinterpret_cast<const float(*)[8]>(&o[8]), valid);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) zc[i] = zn[i];
+        for (int i = 0; i < 8; ++i)
+          zr[8 * b + i] = soft_threshold(__fsub_rn(zr[8 * b + i], __uint_as_float(u[i] ^ usign)), tt[i]);
+        stg256_pred(zs + 8 * b, *reinterpret_cast<const float(*)[8]>(&zr[8 * b]), valid);
       }
-      {   // tail: columns 80..87
-        uint32_t u[8];
-        tmem_ld8(dcol + 80, u);
-        tmem_wait_ld();
-        tc_fence_before();                         // accumulator fully read: hand the TMEM slot back to the MMA warp
-        __syncwarp();
-        if (lane == 0) { if (rank == 0) mbar_arrive(&dempty[ds]); else mbar_arrive_cluster(&dempty[ds], 0); }
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = soft_threshold(__fsub_rn(zc[i], __uint_as_float(u[i] ^ usign)), sTau[m0 + 80 + i]);
-        stg256_pred(zs + 80, o, valid);
-      }
+      tc_fence_before();                           // accumulator fully read: hand the TMEM slot back to the MMA warp
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) mbar_arrive(&dempty[ds]); else mbar_arrive_cluster(&dempty[ds], 0); }
     }
   } else {
     // ============================== MMA issue (leader CTA, one thread) ==============================

@@ -210,7 +210,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  long long tw0 = 0, tw1 = 0, tw2 = 0;
+  long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0, tw5 = 0;
   const long long tstart = clock64();
 
   if (tid == 0) {
@@ -265,6 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     };
     int it = 0;
     uint32_t gch = 0;
+    float r0[32], r1[32], r2[24];
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       int n, qd, qh0, qw0;
       syn_tile_coords(p, tile, n, qd, qh0, qw0);
@@ -280,39 +281,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
           bulk_prefetch_l2(p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02) * kKB, (uint32_t)nq * kKB * 4);
         }
       }
-      // software pipeline: the 32 (24) subbands of K-chunk g+1 are requested before chunk g is converted
-      float vn[32];
-      auto request = [&](int pcn) {
-        const int cn = pcn % 3;
-        const float* src = zs + (cn < 2 ? cn * 64 + half * 32 : 128 + half * 24);
+      // This thread's 88 subbands (its half of the three K-chunks: 32 + 32 + 24) live in registers for the whole tile:
+      // converted to tf32 once, stored to TMEM in both passes.  Right after a group's pass-1 store its registers are
+      // reloaded with the NEXT tile's values, so every load has >= 2 chunk periods to land.
+      if (it == 0) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ldg256_pred(src + 8 * i, *reinterpret_cast<float(*)[8]>(&vn[8 * i]), valid);
-        ldg256_pred(src + 24, *reinterpret_cast<float(*)[8]>(&vn[24]), valid && cn < 2);
-      };
-      request(0);
-#pragma unroll 1
+        for (int i = 0; i < 4; ++i) ldg256_pred(zs + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r0[8 * i]), valid);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ldg256_pred(zs + 64 + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r1[8 * i]), valid);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ldg256_pred(zs + 128 + half * 24 + 8 * i, *reinterpret_cast<float(*)[8]>(&r2[8 * i]), valid);
+      }
+      // coordinates of the next tile (for the register reload)
+      const float* zs2 = zs;
+      int valid2 = 0;
+      if (tile + npairs < p.ntiles) {
+        int n2, qd2, qh02, qw02;
+        syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
+        const int qh2 = qh02 + rank * kTH + quad, qw2 = qw02 + lane;
+        valid2 = qh2 < g.Qh && qw2 < g.Qw;
+        zs2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kKB;
+      }
+#pragma unroll
       for (int pc = 0; pc < 6; ++pc, ++gch) {                    // 2 passes x 3 K-chunks (64, 64, 48 subbands)
         const int c = pc % 3;
         const uint32_t slot = gch & 1;
         const uint32_t acol = lane_addr + kColAB + slot * kASlotB;
-        uint32_t b[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) b[i] = tf32_rna_bits(vn[i]);
-        if (pc < 5) request(pc + 1);
+        if (pc < 3) {                                            // first use of the group: round to tf32 in place
+          if (c == 0) { for (int i = 0; i < 32; ++i) r0[i] = __uint_as_float(tf32_rna_bits(r0[i])); }
+          else if (c == 1) { for (int i = 0; i < 32; ++i) r1[i] = __uint_as_float(tf32_rna_bits(r1[i])); }
+          else { for (int i = 0; i < 24; ++i) r2[i] = __uint_as_float(tf32_rna_bits(r2[i])); }
+        }
         CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));
         tc_fence_after();
-        if (c < 2) {
-          tmem_st32(acol + half * 32, b);
-        } else {
-          tmem_st16(acol + half * 24, *reinterpret_cast<const uint32_t(*)[16]>(&b[0]));
-          tmem_st8(acol + half * 24 + 16, *reinterpret_cast<const uint32_t(*)[8]>(&b[16]));
+        if (c == 0) tmem_st32(acol + half * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r0[0]));
+        else if (c == 1) tmem_st32(acol + half * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r1[0]));
+        else {
+          tmem_st16(acol + half * 24, *reinterpret_cast<const uint32_t(*)[16]>(&r2[0]));
+          tmem_st8(acol + half * 24 + 16, *reinterpret_cast<const uint32_t(*)[8]>(&r2[16]));
         }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); }
+        CDL_TW(tw4, tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
+        if (pc >= 3) {                                           // group is dead for this tile: refill it for the next one
+          if (c == 0) { for (int i = 0; i < 4; ++i) ldg256_pred(zs2 + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r0[8 * i]), valid2); }
+          else if (c == 1) { for (int i = 0; i < 4; ++i) ldg256_pred(zs2 + 64 + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r1[8 * i]), valid2); }
+          else { for (int i = 0; i < 3; ++i) ldg256_pred(zs2 + 128 + half * 24 + 8 * i, *reinterpret_cast<float(*)[8]>(&r2[8 * i]), valid2); }
+        }
       }
-      if (it > 0) flush_tile(tile - npairs, it - 1);
+      CDL_TW(tw5, if (it > 0) flush_tile(tile - npairs, it - 1));
     }
     if (it > 0) flush_tile(pair + (it - 1) * npairs, it - 1);      // footprint of the last tile
   } else if (warp < kMmaWarp) {
@@ -369,7 +384,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   }
   if (p.dbg && lane == 0) {
     long long* d = p.dbg + ((size_t)blockIdx.x * 16 + warp) * 8;
-    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2;
+    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2; d[4] = tw3; d[5] = tw4; d[6] = tw5;
   }
   tc_fence_before();
   cluster_sync_all();

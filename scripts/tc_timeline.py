@@ -43,7 +43,7 @@ def show(name, roles):
 
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); plan.synthesis_step(4, z, r, yp, None, residual=True); e1.record()
-show("synthesis", [("producer", list(range(0, 8)), ["wait aempty", "-", "-"]),
+show("synthesis", [("producer", list(range(0, 8)), ["wait aempty", "wait xfull", "cvt(+ld wait)", "request", "st+arrive", "flush total"]),
                    ("epilogue", list(range(8, 12)), ["wait dfull", "flush+bars", "-"]),
                    ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
 print("   launch ms", e0.elapsed_time(e1))
