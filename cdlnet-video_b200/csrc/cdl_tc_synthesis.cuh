@@ -44,6 +44,7 @@ struct SynTcParams {
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
   const float* wpack;   // this layer: [2 ranks][2 passes][22 k-steps][11 groups][2][8][4]
   int tiles_w, tiles_h, ntiles;
+  int a_lo;             // 0: A = rna_tf32(z) ; 1: A = rna_tf32(z - rna_tf32(z))  (low part, used by the 3-term final synthesis)
   long long* dbg;
 };
 
@@ -53,7 +54,7 @@ constexpr size_t kSynSmemBytes = kSynSmemB + kSynSmemX + 256;
 
 // filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[pass][n = 7*row + tw, k = m], per-rank UMMA layout, tf32 RNE.
 // Pass 0 holds rows 0..24, pass 1 rows 25..48 of the (th,td) row list (th-major); unused columns are zero.
-__global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restrict__ out, int M) {
+__global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restrict__ out, int M, int lo) {
   const int per_rank = 2 * kKBSteps * (kNBP / 2) * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += gridDim.x * blockDim.x) {
     const int rank = i / per_rank;
@@ -71,7 +72,8 @@ __global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restri
       const int th = row / 7, td = row % 7;
       v = w[(size_t)m * kTaps + (td * 7 + th) * 7 + tw];
     }
-    out[i] = ptx::to_tf32_rna(v);
+    const float hi = ptx::to_tf32_rna(v);
+    out[i] = lo ? ptx::to_tf32_rna(v - hi) : hi;                // lo: the part of W that tf32 rounding drops
   }
 }
 
@@ -263,6 +265,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       __syncwarp();
       if (lane == 0) mbar_arrive(&xfree[xb]);
     };
+    const int a_lo = p.a_lo;
+    auto cvt_a = [a_lo](float x) {
+      const float hi = __uint_as_float(tf32_rna_bits(x));
+      return a_lo ? __uint_as_float(tf32_rna_bits(x - hi)) : hi;
+    };
     int it = 0;
     uint32_t gch = 0;
     float r0[32], r1[32], r2[24];
@@ -308,9 +315,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
         const uint32_t slot = gch & 1;
         const uint32_t acol = lane_addr + kColAB + slot * kASlotB;
         if (pc < 3) {                                            // first use of the group: round to tf32 in place
-          if (c == 0) { for (int i = 0; i < 32; ++i) r0[i] = __uint_as_float(tf32_rna_bits(r0[i])); }
-          else if (c == 1) { for (int i = 0; i < 32; ++i) r1[i] = __uint_as_float(tf32_rna_bits(r1[i])); }
-          else { for (int i = 0; i < 24; ++i) r2[i] = __uint_as_float(tf32_rna_bits(r2[i])); }
+          if (c == 0) { for (int i = 0; i < 32; ++i) r0[i] = cvt_a(r0[i]); }
+          else if (c == 1) { for (int i = 0; i < 32; ++i) r1[i] = cvt_a(r1[i]); }
+          else { for (int i = 0; i < 24; ++i) r2[i] = cvt_a(r2[i]); }
         }
         CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));
         tc_fence_after();
