@@ -1,0 +1,249 @@
+"""Temporal sharding of ONE long clip across ranks (BASELINE config 5).
+
+The reference never does this (it chops videos into independent 16-frame windows, analyze3d.py:62,105);
+the module's forward, however, is defined for any clip length, and this driver computes exactly that
+forward with the coarse time axis split into contiguous slabs, one per rank:
+
+  * rank r owns coarse frames [q0, q1) and keeps the fine frames [s*q0 - hf, s*q1 + hb) resident, where
+    hf = Pd//2 at a seam (0 at the clip start) and hb = Pd//2 - s + 1 at a seam (0 at the clip end);
+  * its uncropped synthesis  B z_local  covers exactly that range; on the Pd - s frames it shares with a
+    neighbour both ranks hold partial sums, so once per iteration (and once for D z) the two exchange those
+    frames (P2P send/recv, ring neighbours only) and add them - image-domain halos, 25x smaller than a
+    z-domain halo;
+  * the per-sample mean of pre_process_3d needs one all-reduce of per-rank fp64 sums.
+
+`SlabRank` holds one rank's state and is written against a small `ops` interface so that the same driver
+logic runs on the CUDA plan (`PlanOps`) and, in the CPU tests, on the oracle (`tests/test_sharded_cpu.py`).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(Qd_total: int, world: int, rank: int):
+    """Contiguous, near-equal split of the coarse frames."""
+    base, rem = divmod(Qd_total, world)
+    q0 = rank * base + min(rank, rem)
+    q1 = q0 + base + (1 if rank < rem else 0)
+    return q0, q1
+
+
+def slab_geometry(D: int, Pd: int, s: int, world: int, rank: int):
+    """-> dict(q0, q1, hf, hb, f0, f1): owned coarse frames, halos, resident fine range [f0, f1)."""
+    if D % s:
+        raise ValueError("temporal sharding needs D divisible by the stride (no temporal stride padding at seams)")
+    Qd = D // s
+    if Qd < world:
+        raise ValueError("fewer coarse frames than ranks")
+    q0, q1 = slab_bounds(Qd, world, rank)
+    h = Pd // 2
+    hf = h if rank > 0 else 0
+    hb = (h - s + 1) if rank < world - 1 else 0
+    if min(b - a for a, b in (slab_bounds(Qd, world, r) for r in range(world))) * s < Pd:
+        raise ValueError("slabs are thinner than the temporal filter extent")
+    return dict(q0=q0, q1=q1, hf=hf, hb=hb, f0=s * q0 - hf, f1=s * q1 + hb, overlap=Pd - s)
+
+
+class PlanOps:
+    """The slab operators on one GPU: a libcdl_b200 plan with temporal halos (no fallback)."""
+
+    def __init__(self, plan, sum_plan):
+        self.plan, self.sum_plan = plan, sum_plan
+
+    def owned_sums(self, y_owned):                    # (2N,) float64: sum(y), count
+        return self.sum_plan.reduce_sums(y_owned.contiguous())
+
+    def mean_from_sums(self, sums):
+        return self.plan.mean_from_sums(sums)
+
+    def center_pad(self, y_loc, mean):
+        return self.plan.center_pad(y_loc.contiguous(), mean)[0]
+
+    def new_code(self):
+        return self.plan.new_code()
+
+    def new_fine(self):
+        return torch.empty(self.plan.fine_shape, dtype=torch.float32, device=self.plan.device)
+
+    def analysis(self, k, r, code, c, first):
+        self.plan.analysis_step(k, r, code, c, first=first)
+
+    def synthesis(self, k, code, out, yp, residual):
+        self.plan.synthesis_step(k, code, out, yp, None, residual=residual)
+
+    def postprocess(self, xp, mean):
+        return self.plan.postprocess(xp, mean)
+
+    def export_code(self, code):
+        return self.plan.export_code(code)
+
+
+class SlabRank:
+    """One rank's share of the forward pass.  Phases are separate methods so that a driver can interleave the
+    neighbour exchange (distributed) or run several ranks in lock step inside one process (tests)."""
+
+    def __init__(self, ops, geo, K, s):
+        self.ops, self.geo, self.K, self.s = ops, geo, K, s
+        self.ov = geo["overlap"]
+
+    # -- preprocess --------------------------------------------------------------------------------
+    def local_sums(self, y_loc):
+        g = self.geo
+        owned = y_loc[:, :, g["hf"]:y_loc.shape[2] - g["hb"]]
+        self.y_loc = y_loc
+        return self.ops.owned_sums(owned)
+
+    def set_global_sums(self, sums, c):
+        self.mean = self.ops.mean_from_sums(sums)
+        self.yp = self.ops.center_pad(self.y_loc, self.mean)
+        self.c = c
+        self.code = self.ops.new_code()
+        self.r = self.ops.new_fine()
+
+    # -- iterations ----------------------------------------------------------------------------------
+    def first(self):
+        self.ops.analysis(0, self.yp, self.code, self.c, True)
+
+    def synth(self, k, residual=True):
+        """Local partial B_k z (minus yp when residual); returns the (head, tail) overlap slices to send."""
+        self.ops.synthesis(k, self.code, self.r, self.yp if residual else None, residual)
+        self._residual = residual
+        return self._head(self.r), self._tail(self.r)
+
+    def _head(self, t):
+        return t[:, :, :self.ov] if self.geo["hf"] else None
+
+    def _tail(self, t):
+        return t[:, :, t.shape[2] - self.ov:] if self.geo["hb"] else None
+
+    def add_halo(self, recv_prev, recv_next):
+        """r_overlap = mine + theirs (+ yp: both partials already carry -yp in residual mode)."""
+        if recv_prev is not None:
+            h = self._head(self.r)
+            h.add_(recv_prev)
+            if self._residual:
+                h.add_(self._head(self.yp))
+        if recv_next is not None:
+            t = self._tail(self.r)
+            t.add_(recv_next)
+            if self._residual:
+                t.add_(self._tail(self.yp))
+
+    def ana(self, k):
+        self.ops.analysis(k, self.r, self.code, self.c, False)
+
+    def finish(self):
+        """After the final synth(0, residual=False) + add_halo: crop to the owned frames."""
+        x = self.ops.postprocess(self.r, self.mean)
+        g = self.geo
+        return x[:, :, g["hf"]:x.shape[2] - g["hb"]], self.ops.export_code(self.code)
+
+
+# ------------------------------------------------------------------------------------------------
+# drivers
+# ------------------------------------------------------------------------------------------------
+def run_lockstep(ranks, y_slabs, c):
+    """All ranks inside one process (single-GPU emulation / CPU tests): the exchange is a tensor hand-over."""
+    sums = [r.local_sums(y) for r, y in zip(ranks, y_slabs)]
+    total = sum(s.double() for s in sums)
+    for r in ranks:
+        r.set_global_sums(total.clone(), c)
+
+    def exchange(pairs):
+        heads = [p[0] for p in pairs]
+        tails = [p[1] for p in pairs]
+        snap_h = [h.clone() if h is not None else None for h in heads]
+        snap_t = [t.clone() if t is not None else None for t in tails]
+        for i, r in enumerate(ranks):
+            r.add_halo(snap_t[i - 1] if i > 0 else None, snap_h[i + 1] if i + 1 < len(ranks) else None)
+
+    for r in ranks:
+        r.first()
+    K = ranks[0].K
+    for k in range(1, K):
+        exchange([r.synth(k, True) for r in ranks])
+        for r in ranks:
+            r.ana(k)
+    exchange([r.synth(0, False) for r in ranks])
+    outs = [r.finish() for r in ranks]
+    return torch.cat([o[0] for o in outs], dim=2), torch.cat([o[1] for o in outs], dim=2)
+
+
+class DistExchange:
+    """Neighbour exchange over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce_sums(self, sums):
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        return sums
+
+    def halo(self, head, tail):
+        ops, recv_prev, recv_next = [], None, None
+        if head is not None:
+            recv_prev = torch.empty_like(head)
+            send = head.contiguous()
+            ops += [dist.P2POp(dist.isend, send, self.rank - 1, self.group), dist.P2POp(dist.irecv, recv_prev, self.rank - 1, self.group)]
+        if tail is not None:
+            recv_next = torch.empty_like(tail)
+            send = tail.contiguous()
+            ops += [dist.P2POp(dist.isend, send, self.rank + 1, self.group), dist.P2POp(dist.irecv, recv_next, self.rank + 1, self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return recv_prev, recv_next
+
+
+def run_distributed(rank_state, y_slab, c, xch: DistExchange):
+    """One rank of the distributed forward.  Returns (xhat of the owned frames, z of the owned coarse frames)."""
+    sums = xch.all_reduce_sums(rank_state.local_sums(y_slab).double())
+    rank_state.set_global_sums(sums, c)
+    rank_state.first()
+    for k in range(1, rank_state.K):
+        head, tail = rank_state.synth(k, True)
+        rank_state.add_halo(*xch.halo(head, tail))
+        rank_state.ana(k)
+    head, tail = rank_state.synth(0, False)
+    rank_state.add_halo(*xch.halo(head, tail))
+    return rank_state.finish()
+
+
+class ShardedVideoDenoiser:
+    """Convenience wrapper: one long clip (N,1,D,H,W) over `world` GPUs, one process per GPU.
+
+        den = ShardedVideoDenoiser(net, clip_shape, rank, world, device)
+        xhat_owned, z_owned = den(y_slab, sigma)          # y_slab = clip frames den.geo["f0"]:den.geo["f1"]
+    """
+
+    def __init__(self, net, clip_shape, rank, world, device, precision="tf32", group=None):
+        from .plan import Plan
+        N, C, D, H, W = clip_shape
+        P3 = net._P3()
+        self.geo = slab_geometry(D, P3[0], net.s, world, rank)
+        g = self.geo
+        dev_index = torch.device(device).index or 0
+        plan = Plan(3, N, C, net.M, net.K, (g["f1"] - g["f0"], H, W), P3, net.s, precision=precision, device=dev_index,
+                    halo_front=g["hf"], halo_back=g["hb"])
+        sum_plan = Plan(3, N, C, net.M, 1, (net.s * (g["q1"] - g["q0"]), H, W), P3, net.s, precision="fp32", device=dev_index)
+        A, B = net._filter_banks()
+        plan.set_weights(A, B, net.t)
+        self.net, self.plan = net, plan
+        self.state = SlabRank(PlanOps(plan, sum_plan), g, net.K, net.s)
+        self.xch = DistExchange(group) if world > 1 else None
+        self.world = world
+
+    def __call__(self, y_slab, sigma=None):
+        c = self.net._c_vector(sigma, y_slab.shape[0], y_slab.device)
+        if self.world == 1:
+            st = self.state
+            st.set_global_sums(st.local_sums(y_slab).double(), c)
+            st.first()
+            for k in range(1, st.K):
+                st.synth(k, True)
+                st.ana(k)
+            st.synth(0, False)
+            return st.finish()
+        return run_distributed(self.state, y_slab, c, self.xch)
