@@ -232,7 +232,7 @@ class ShardedVideoDenoiser:
         plan.set_weights(A, B, net.t)
         self.net, self.plan = net, plan
         self.state = SlabRank(PlanOps(plan, sum_plan), g, net.K, net.s)
-        self.xch = DistExchange(group) if world > 1 else None
+        self.group, self.xch = group, None          # the exchange is created on first use (needs an initialised process group)
         self.world = world
 
     def __call__(self, y_slab, sigma=None):
@@ -246,4 +246,6 @@ class ShardedVideoDenoiser:
                 st.ana(k)
             st.synth(0, False)
             return st.finish()
+        if self.xch is None:
+            self.xch = DistExchange(self.group)
         return run_distributed(self.state, y_slab, c, self.xch)
