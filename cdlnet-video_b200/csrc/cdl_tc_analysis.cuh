@@ -152,20 +152,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         tc_fence_after();
         const uint32_t acol = lane_addr + kColA + slot * kASlot;
         if (ch < kChunks - 1) {
-          uint32_t v[56];
+          // phase 1: all 32 window loads of the chunk's 8 (td,th) rows are issued back to back (raw[8*rr .. +7] =
+          // fine w = 2q-4 .. 2q+3); phase 2: round the 7 taps of each row in registers
+          float raw[64];
 #pragma unroll
           for (int rr = 0; rr < kChunkRows; ++rr) {
             const int row = ch * kChunkRows + rr, td = row / kP, th = row % kP;
-            const float2* src = reinterpret_cast<const float2*>(rs + (td * kRH + th) * kRW);
-            float2 a = src[0], b = src[1], c = src[2], d = src[3];      // fine w = 2q-4 .. 2q+3 ; taps use 2q-3 .. 2q+3
-            v[rr * 7 + 0] = tf32_rna_bits(a.y);
-            v[rr * 7 + 1] = tf32_rna_bits(b.x);
-            v[rr * 7 + 2] = tf32_rna_bits(b.y);
-            v[rr * 7 + 3] = tf32_rna_bits(c.x);
-            v[rr * 7 + 4] = tf32_rna_bits(c.y);
-            v[rr * 7 + 5] = tf32_rna_bits(d.x);
-            v[rr * 7 + 6] = tf32_rna_bits(d.y);
+            const float* src = rs + (td * kRH + th) * kRW;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lds64(src + 2 * j, raw[8 * rr + 2 * j], raw[8 * rr + 2 * j + 1]);
           }
+          uint32_t v[56];
+#pragma unroll
+          for (int rr = 0; rr < kChunkRows; ++rr)
+#pragma unroll
+            for (int tw = 0; tw < 7; ++tw) v[rr * 7 + tw] = tf32_rna_bits(raw[8 * rr + 1 + tw]);
           tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&v[0]));
           tmem_st16(acol + 32, *reinterpret_cast<const uint32_t(*)[16]>(&v[32]));
           tmem_st8(acol + 48, *reinterpret_cast<const uint32_t(*)[8]>(&v[48]));

@@ -209,6 +209,10 @@ __device__ __forceinline__ void stg256_pred(float* p, const float (&v)[8], int o
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t@p st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};\n\t}"
                ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p), "r"(ok) : "memory");
 }
+// volatile shared-memory 8-byte load: keeps its place in program order, so a run of them is issued back to back
+__device__ __forceinline__ void lds64(const float* p, float& a, float& b) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(smem_u32(p)));
+}
 // tf32 round-to-nearest (ties away) as two integer ops; inf/nan are not special-cased (z and r are finite)
 __device__ __forceinline__ uint32_t tf32_rna_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ float to_tf32_rna(float x) {   // round-to-nearest (ties away) to 10-bit mantissa
