@@ -3,7 +3,8 @@
 //     z <- ST(z - A_k r, t0 + c*t1)            (reference model/net.py:200,205 + :11-14)
 //
 // as an implicit GEMM  U[q, m] = sum_t R[q, t] * W[m, t]  with  M_gemm = 256 coarse sites per CTA pair,
-// N = 176 (169 subbands, zero padded), K = 344 (343 taps + 1 zero column), kind::tf32, fp32 accumulation.
+// N = 176 (169 subbands, zero padded), K = 392 (49 (td,th) rows x 8: the 7 w-taps plus the 8-byte-aligned window's
+// first element, whose filter column is zero), kind::tf32, fp32 accumulation.
 //
 //   * cta_group::2: the two CTAs of a cluster own 128 coarse sites each (a 1 x 4 x 32 block) and share
 //     the filter bank: each keeps HALF of it (88 subbands x 344 taps = 121 KB) resident in shared memory
@@ -31,9 +32,9 @@ constexpr int kMmaWarp = 12;
 constexpr int kNA = 176;                 // GEMM N of the analysis (subbands, padded)
 constexpr int kNAH = kNA / 2;            // per-CTA half of the filter bank
 constexpr int kP = 7, kTaps = 343;
-constexpr int kKSteps = 43;              // ceil(343 / 8) tf32 MMA K-steps
-constexpr int kChunkRows = 8;            // (td,th) rows per A chunk -> 56 columns = 7 K-steps
-constexpr int kChunks = 7;               // 6 full chunks + 1 chunk of one row (7 taps + 1 zero column)
+constexpr int kKSteps = 49;              // one tf32 MMA K-step (8 columns) per (td,th) row: window element 0 (zero filter) + 7 taps
+constexpr int kChunkRows = 8;            // (td,th) rows per A chunk -> 64 columns = 8 K-steps
+constexpr int kChunks = 7;               // 6 full chunks + 1 chunk of one row
 constexpr int kTH = 4, kTW = 32;         // coarse tile per CTA: 1 x 4 x 32 (d,h,w); a pair stacks two along h
 constexpr int kRD = 7, kRH = 2 * (kTH - 1) + kP, kRW = 72;   // residual halo tile (fine): 7 x 13 x 72 floats
 constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats = 26208 B (one TMA box)
@@ -65,8 +66,8 @@ __global__ void k_pack_tc_analysis(const float* __restrict__ w, float* __restric
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int e = i % 4, r8 = (i / 4) % 8, kc = (i / 32) % 2, grp = (i / 64) % (kNAH / 8);
     int ks = (i / (kNAH * 8)) % kKSteps, rank = i / (kNAH * 8 * kKSteps);
-    int m = rank * kNAH + grp * 8 + r8, k = ks * 8 + kc * 4 + e;
-    float v = (m < M && k < kTaps) ? w[(size_t)m * kTaps + k] : 0.0f;
+    int m = rank * kNAH + grp * 8 + r8, j = kc * 4 + e;              // k-step ks = (td,th) row; column j: 0 = pad, 1..7 = tw 0..6
+    float v = (m < M && j > 0) ? w[(size_t)m * kTaps + ks * 7 + (j - 1)] : 0.0f;
     out[i] = ptx::to_tf32_rna(v);
   }
 }
@@ -114,10 +115,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
     sT[kNA + i] = (i < g.M) ? p.t1[i] : 0.0f;
   }
   __syncthreads();
-  if (tid == 0) {   // this CTA's half of the filter bank: 121088 B in 4 bulk copies
+  if (tid == 0) {   // this CTA's half of the filter bank: 137984 B in 4 bulk copies
     mbar_expect_tx(wbar, (uint32_t)kAnaSmemB);
     const char* src = reinterpret_cast<const char*>(p.wpack) + (size_t)rank * kAnaSmemB;
-    const uint32_t piece = 30272;   // 121088 / 4, multiple of 16
+    const uint32_t piece = (uint32_t)(kAnaSmemB / 4);   // 34496, multiple of 16
     for (int i = 0; i < 4; ++i) bulk_g2s(reinterpret_cast<char*>(sB) + i * piece, src + i * piece, piece, wbar);
   }
   tc_fence_before();
@@ -143,42 +144,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
       const int buf = it & 1;
       CDL_TW(tw1, mbar_wait(&rfull[buf], (it >> 1) & 1); named_bar_sync(1, 128));   // tile `it` landed; everyone left tile it-1
       if (tid == 0 && tile + npairs < p.ntiles) issue_tile_load(tile + npairs, buf ^ 1);
+      // round the tile to tf32 (RNE) once, in place: every element is used by ~43 windows, and the tensor core would
+      // truncate.  After this the im2col expansion is pure data movement.
+      {
+        float4* t4 = reinterpret_cast<float4*>(sR + buf * kRTilePad);
+        for (int i = tid; i < kRTile / 4; i += 128) {
+          float4 v = t4[i];
+          v.x = __uint_as_float(tf32_rna_bits(v.x)); v.y = __uint_as_float(tf32_rna_bits(v.y));
+          v.z = __uint_as_float(tf32_rna_bits(v.z)); v.w = __uint_as_float(tf32_rna_bits(v.w));
+          t4[i] = v;
+        }
+        fence_async_smem();                       // generic-proxy writes ordered before the TMA that later refills this buffer
+        named_bar_sync(1, 128);
+      }
       // this thread's coarse site: row `warp` of the CTA tile, column `lane`
       const float* rs = sR + buf * kRTilePad + (2 * warp) * kRW + 2 * lane;
 #pragma unroll
       for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
         const uint32_t slot = gchunk & 1;
-        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gchunk >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t acol = lane_addr + kColA + slot * kASlot;
-        if (ch < kChunks - 1) {
-          // phase 1: all 32 window loads of the chunk's 8 (td,th) rows are issued back to back (raw[8*rr .. +7] =
-          // fine w = 2q-4 .. 2q+3); phase 2: round the 7 taps of each row in registers
-          float raw[64];
+        // the 8-float window (fine w = 2q-4 .. 2q+3) of each (td,th) row goes to TMEM as is: 8 columns = one K-step
+        float raw[64];
+        constexpr int kRowsLast = 1;
+        const int nrows = (ch < kChunks - 1) ? kChunkRows : kRowsLast;
 #pragma unroll
-          for (int rr = 0; rr < kChunkRows; ++rr) {
+        for (int rr = 0; rr < kChunkRows; ++rr) {
+          if (rr < nrows) {
             const int row = ch * kChunkRows + rr, td = row / kP, th = row % kP;
             const float* src = rs + (td * kRH + th) * kRW;
 #pragma unroll
             for (int j = 0; j < 4; ++j) lds64(src + 2 * j, raw[8 * rr + 2 * j], raw[8 * rr + 2 * j + 1]);
           }
-          uint32_t v[56];
-#pragma unroll
-          for (int rr = 0; rr < kChunkRows; ++rr)
-#pragma unroll
-            for (int tw = 0; tw < 7; ++tw) v[rr * 7 + tw] = tf32_rna_bits(raw[8 * rr + 1 + tw]);
-          tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&v[0]));
-          tmem_st16(acol + 32, *reinterpret_cast<const uint32_t(*)[16]>(&v[32]));
-          tmem_st8(acol + 48, *reinterpret_cast<const uint32_t(*)[8]>(&v[48]));
+        }
+        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gchunk >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t acol = lane_addr + kColA + slot * kASlot;
+        if (ch < kChunks - 1) {
+          tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&raw[0]));
+          tmem_st32(acol + 32, *reinterpret_cast<const uint32_t(*)[32]>(&raw[32]));
         } else {
-          uint32_t v[8];
-          const float2* src = reinterpret_cast<const float2*>(rs + (6 * kRH + 6) * kRW);
-          float2 a = src[0], b = src[1], c = src[2], d = src[3];
-          v[0] = tf32_rna_bits(a.y); v[1] = tf32_rna_bits(b.x);
-          v[2] = tf32_rna_bits(b.y); v[3] = tf32_rna_bits(c.x);
-          v[4] = tf32_rna_bits(c.y); v[5] = tf32_rna_bits(d.x);
-          v[6] = tf32_rna_bits(d.y); v[7] = 0u;
-          tmem_st8(acol, v);
+          tmem_st8(acol, *reinterpret_cast<const uint32_t(*)[8]>(&raw[0]));
         }
         CDL_TW(tw2, tmem_wait_st());
         CDL_TW(tw4, tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
@@ -267,10 +271,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
           CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gchunk >> 1) & 1));
           tc_fence_after();
           const uint32_t a0 = tbase + kColA + slot * kASlot;
-          uint64_t bdesc = bdesc0 + (uint64_t)(ch * 7) * kBStep;      // descriptor start-address field advances by kBStep per k-step
+          uint64_t bdesc = bdesc0 + (uint64_t)(ch * kChunkRows) * kBStep;   // descriptor start-address field advances by kBStep per k-step
           if (ch < kChunks - 1) {
 #pragma unroll
-            for (int j = 0; j < 7; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bdesc + (uint64_t)j * kBStep, idesc, (ch | j) != 0);
+            for (int j = 0; j < kChunkRows; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bdesc + (uint64_t)j * kBStep, idesc, (ch | j) != 0);
           } else {
             mma_tf32_ts<2>(dcol, a0, bdesc, idesc, 1);
           }
