@@ -33,13 +33,14 @@ constexpr int kNA = 176;                 // GEMM N of the analysis (subbands, pa
 constexpr int kNAH = kNA / 2;            // per-CTA half of the filter bank
 constexpr int kP = 7, kTaps = 343;
 constexpr int kKSteps = 49;              // one tf32 MMA K-step (8 columns) per (td,th) row: window element 0 (zero filter) + 7 taps
-constexpr int kChunkRows = 8;            // (td,th) rows per A chunk -> 64 columns = 8 K-steps
-constexpr int kChunks = 7;               // 6 full chunks + 1 chunk of one row
+constexpr int kChunkRows = 4;            // (td,th) rows per A chunk -> 32 columns = 4 K-steps
+constexpr int kChunks = 13;              // 12 full chunks + 1 chunk of one row
+constexpr int kASlots = 4;               // A ring depth: covers the producer -> MMA -> producer hand-shake latency
 constexpr int kTH = 4, kTW = 32;         // coarse tile per CTA: 1 x 4 x 32 (d,h,w); a pair stacks two along h
 constexpr int kRD = 7, kRH = 2 * (kTH - 1) + kP, kRW = 72;   // residual halo tile (fine): 7 x 13 x 72 floats
 constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats = 26208 B (one TMA box)
 constexpr int kRTilePad = 6560;          // buffer pitch: 26240 B, a multiple of 128 B (TMA destination alignment)
-constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 64;   // TMEM columns: D0 | D1 | A0 | A1  (480 of 512)
+constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 32;   // TMEM columns: D0 | D1 | A0..A3  (480 of 512)
 
 struct AnaTcParams {
   Geo g;
@@ -87,26 +88,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
   float* sT = reinterpret_cast<float*>(smem_raw + kAnaSmemB + kAnaSmemR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kAnaSmemB + kAnaSmemR + kAnaSmemT);
   uint64_t* wbar = bars + 0;
-  uint64_t* afull = bars + 1;    // [2]  (used in the leader CTA) producers of both CTAs -> MMA
-  uint64_t* aempty = bars + 3;   // [2]  MMA commit (multicast) -> producers
-  uint64_t* dfull = bars + 5;    // [2]  MMA commit (multicast) -> epilogue
-  uint64_t* dempty = bars + 7;   // [2]  (leader) epilogue warps of both CTAs -> MMA
-  uint64_t* wready = bars + 9;   //      (leader) the peer CTA's filters have landed
-  uint64_t* rfull = bars + 10;   // [2]  TMA: residual halo tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* afull = bars + 1;    // [4]  (used in the leader CTA) producers of both CTAs -> MMA
+  uint64_t* aempty = bars + 5;   // [4]  MMA commit (multicast) -> producers
+  uint64_t* dfull = bars + 9;    // [2]  MMA commit (multicast) -> epilogue
+  uint64_t* dempty = bars + 11;  // [2]  (leader) epilogue warps of both CTAs -> MMA
+  uint64_t* wready = bars + 13;  //      (leader) the peer CTA's filters have landed
+  uint64_t* rfull = bars + 14;   // [2]  TMA: residual halo tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0;
+  long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0, tw5 = 0;
   const long long tstart = clock64();
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
     for (int i = 0; i < 2; ++i) mbar_init(&rfull[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 16); }
+    for (int i = 0; i < kASlots; ++i) { mbar_init(&afull[i], 8); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 16); }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
@@ -161,9 +163,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
       const float* rs = sR + buf * kRTilePad + (2 * warp) * kRW + 2 * lane;
 #pragma unroll
       for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
-        const uint32_t slot = gchunk & 1;
+        const uint32_t slot = gchunk % kASlots;
         // the 8-float window (fine w = 2q-4 .. 2q+3) of each (td,th) row goes to TMEM as is: 8 columns = one K-step
-        float raw[64];
+        float raw[8 * kChunkRows];
         constexpr int kRowsLast = 1;
         const int nrows = (ch < kChunks - 1) ? kChunkRows : kRowsLast;
 #pragma unroll
@@ -175,12 +177,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
             for (int j = 0; j < 4; ++j) lds64(src + 2 * j, raw[8 * rr + 2 * j], raw[8 * rr + 2 * j + 1]);
           }
         }
-        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gchunk >> 1) & 1) ^ 1));
+        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gchunk / kASlots) & 1) ^ 1));
         tc_fence_after();
         const uint32_t acol = lane_addr + kColA + slot * kASlot;
         if (ch < kChunks - 1) {
           tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&raw[0]));
-          tmem_st32(acol + 32, *reinterpret_cast<const uint32_t(*)[32]>(&raw[32]));
         } else {
           tmem_st8(acol, *reinterpret_cast<const uint32_t(*)[8]>(&raw[0]));
         }
@@ -267,8 +268,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         tc_fence_after();
         const uint32_t dcol = tbase + kColD + ds * kNA;
         for (int ch = 0; ch < kChunks; ++ch, ++gchunk) {
-          const uint32_t slot = gchunk & 1;
-          CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gchunk >> 1) & 1));
+          const uint32_t slot = gchunk % kASlots;
+          CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gchunk / kASlots) & 1));
           tc_fence_after();
           const uint32_t a0 = tbase + kColA + slot * kASlot;
           uint64_t bdesc = bdesc0 + (uint64_t)(ch * kChunkRows) * kBStep;   // descriptor start-address field advances by kBStep per k-step
@@ -287,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
   }
   if (p.dbg && lane == 0) {
     long long* d = p.dbg + ((size_t)blockIdx.x * 16 + warp) * 8;
-    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2; d[4] = tw3; d[5] = tw4;
+    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2; d[4] = tw3; d[5] = tw4; d[6] = tw5;
   }
   // teardown: everyone done (all MMAs were consumed by the epilogues before they exit)
   tc_fence_before();

@@ -6,7 +6,11 @@
 #include <stdint.h>
 
 // development aid: per-warp cycle counters of the barrier waits (enabled when a debug buffer is set)
+#ifdef CDL_TC_PROFILE
 #define CDL_TW(acc, stmt) do { long long t0__ = clock64(); stmt; acc += clock64() - t0__; } while (0)
+#else
+#define CDL_TW(acc, stmt) do { stmt; } while (0)
+#endif
 
 namespace cdl {
 namespace ptx {

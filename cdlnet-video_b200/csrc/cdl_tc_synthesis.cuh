@@ -34,7 +34,8 @@ constexpr int kKB = 176;                  // GEMM K of the synthesis (subbands, 
 constexpr int kKBSteps = kKB / 8;         // 22
 constexpr int kNBP = 176;                 // GEMM N per pass
 constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in pass 0 (pass 1: 24)
-constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 64;   // TMEM: D0 | D1 | A0 | A1  (480 of 512)
+constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 32;   // TMEM: D0 | D1 | A0..A3  (480 of 512)
+constexpr int kASlotsB = 4;               // A ring depth (32 subbands = 4 K-steps per slot; 6 chunks per pass)
 constexpr int kXD = 7, kXH = 13, kXW = 72;                   // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
 constexpr int kXTile = kXD * kXH * kXW;
 
@@ -199,14 +200,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   float* sX = reinterpret_cast<float*>(smem_raw + kSynSmemB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kSynSmemB + kSynSmemX);
   uint64_t* wbar = bars + 0;
-  uint64_t* afull = bars + 1;    // [2] (leader) producers of both CTAs -> MMA
-  uint64_t* aempty = bars + 3;   // [2] MMA commit (multicast) -> producers
-  uint64_t* dfull = bars + 5;    // [2] MMA commit (multicast) -> epilogue   (index = pass)
-  uint64_t* dempty = bars + 7;   // [2] (leader) epilogue warps of both CTAs -> MMA
-  uint64_t* wready = bars + 9;   //     (leader) the peer CTA's filters have landed
-  uint64_t* xfull = bars + 10;   // [2] epilogue -> producers: footprint tile complete, flush it
-  uint64_t* xfree = bars + 12;   // [2] producers -> epilogue: footprint tile flushed and cleared
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* afull = bars + 1;    // [4] (leader) producers of both CTAs -> MMA
+  uint64_t* aempty = bars + 5;   // [4] MMA commit (multicast) -> producers
+  uint64_t* dfull = bars + 9;    // [2] MMA commit (multicast) -> epilogue   (index = pass)
+  uint64_t* dempty = bars + 11;  // [2] (leader) epilogue warps of both CTAs -> MMA
+  uint64_t* wready = bars + 13;  //     (leader) the peer CTA's filters have landed
+  uint64_t* xfull = bars + 14;   // [2] epilogue -> producers: footprint tile complete, flush it
+  uint64_t* xfree = bars + 16;   // [2] producers -> epilogue: footprint tile flushed and cleared
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -219,7 +220,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 4); mbar_init(&xfree[i], 8); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
+    for (int i = 0; i < kASlotsB; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
@@ -272,7 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     };
     int it = 0;
     uint32_t gch = 0;
-    float r0[32], r1[32], r2[24];
+    float rg[6][16];
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       int n, qd, qh0, qw0;
       syn_tile_coords(p, tile, n, qd, qh0, qw0);
@@ -288,19 +290,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
           bulk_prefetch_l2(p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02) * kKB, (uint32_t)nq * kKB * 4);
         }
       }
-      // This thread's 88 subbands (its half of the three K-chunks: 32 + 32 + 24) live in registers for the whole tile:
-      // converted to tf32 once, stored to TMEM in both passes.  Right after a group's pass-1 store its registers are
-      // reloaded with the NEXT tile's values, so every load has >= 2 chunk periods to land.
+      // This thread's 88 subbands (its half of the six 32-subband K-chunks: 5 x 16 + 8) live in registers for the whole
+      // tile: converted to tf32 once, stored to TMEM in both passes.  Right after a group's pass-1 store its registers
+      // are reloaded with the NEXT tile's values, so every load has several chunk periods to land.
+      auto load_group = [&](float (&dst)[16], const float* base, int c, int ok) {
+        if (c < 5) {
+          ldg256_pred(base + 32 * c + 16 * half, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
+          ldg256_pred(base + 32 * c + 16 * half + 8, *reinterpret_cast<float(*)[8]>(&dst[8]), ok);
+        } else {
+          ldg256_pred(base + 160 + 8 * half, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
+        }
+      };
       if (it == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ldg256_pred(zs + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r0[8 * i]), valid);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ldg256_pred(zs + 64 + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r1[8 * i]), valid);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) ldg256_pred(zs + 128 + half * 24 + 8 * i, *reinterpret_cast<float(*)[8]>(&r2[8 * i]), valid);
+        for (int c = 0; c < 6; ++c) load_group(rg[c], zs, c, valid);
       }
-      // coordinates of the next tile (for the register reload)
-      const float* zs2 = zs;
+      const float* zs2 = zs;                                     // the next tile's site (for the register refill)
       int valid2 = 0;
       if (tile + npairs < p.ntiles) {
         int n2, qd2, qh02, qw02;
@@ -310,29 +315,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
         zs2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kKB;
       }
 #pragma unroll
-      for (int pc = 0; pc < 6; ++pc, ++gch) {                    // 2 passes x 3 K-chunks (64, 64, 48 subbands)
-        const int c = pc % 3;
-        const uint32_t slot = gch & 1;
+      for (int pc = 0; pc < 12; ++pc, ++gch) {                   // 2 passes x 6 K-chunks of 32 subbands (the last holds 16)
+        const int c = pc % 6;
+        const uint32_t slot = gch % kASlotsB;
         const uint32_t acol = lane_addr + kColAB + slot * kASlotB;
-        if (pc < 3) {                                            // first use of the group: round to tf32 in place
-          if (c == 0) { for (int i = 0; i < 32; ++i) r0[i] = cvt_a(r0[i]); }
-          else if (c == 1) { for (int i = 0; i < 32; ++i) r1[i] = cvt_a(r1[i]); }
-          else { for (int i = 0; i < 24; ++i) r2[i] = cvt_a(r2[i]); }
+        if (pc < 6) {                                            // first use of the group: round to tf32 in place
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rg[c][i] = cvt_a(rg[c][i]);
         }
-        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch >> 1) & 1) ^ 1));
+        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch / kASlotsB) & 1) ^ 1));
         tc_fence_after();
-        if (c == 0) tmem_st32(acol + half * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r0[0]));
-        else if (c == 1) tmem_st32(acol + half * 32, *reinterpret_cast<const uint32_t(*)[32]>(&r1[0]));
-        else {
-          tmem_st16(acol + half * 24, *reinterpret_cast<const uint32_t(*)[16]>(&r2[0]));
-          tmem_st8(acol + half * 24 + 16, *reinterpret_cast<const uint32_t(*)[8]>(&r2[16]));
-        }
+        if (c < 5) tmem_st16(acol + 16 * half, *reinterpret_cast<const uint32_t(*)[16]>(&rg[c][0]));
+        else tmem_st8(acol + 8 * half, *reinterpret_cast<const uint32_t(*)[8]>(&rg[c][0]));
         CDL_TW(tw4, tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
-        if (pc >= 3) {                                           // group is dead for this tile: refill it for the next one
-          if (c == 0) { for (int i = 0; i < 4; ++i) ldg256_pred(zs2 + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r0[8 * i]), valid2); }
-          else if (c == 1) { for (int i = 0; i < 4; ++i) ldg256_pred(zs2 + 64 + half * 32 + 8 * i, *reinterpret_cast<float(*)[8]>(&r1[8 * i]), valid2); }
-          else { for (int i = 0; i < 3; ++i) ldg256_pred(zs2 + 128 + half * 24 + 8 * i, *reinterpret_cast<float(*)[8]>(&r2[8 * i]), valid2); }
-        }
+        if (pc >= 6) load_group(rg[c], zs2, c, valid2);          // group is dead for this tile: refill it for the next one
       }
       CDL_TW(tw5, if (it > 0) flush_tile(tile - npairs, it - 1));
     }
@@ -368,18 +364,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
           CDL_TW(tw0, mbar_wait_cluster(&dempty[pass], (it & 1) ^ 1));
           tc_fence_after();
           const uint32_t dcol = tbase + kColDB + pass * kNBP;
-          for (int c = 0; c < 3; ++c, ++gch) {
-            const uint32_t slot = gch & 1;
-            CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gch >> 1) & 1));
+          for (int c = 0; c < 6; ++c, ++gch) {
+            const uint32_t slot = gch % kASlotsB;
+            CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gch / kASlotsB) & 1));
             tc_fence_after();
             const uint32_t a0 = tbase + kColAB + slot * kASlotB;
-            const uint64_t bd = bdesc0 + (uint64_t)(pass * kKBSteps + c * 8) * kBStep;
-            if (c < 2) {
+            const uint64_t bd = bdesc0 + (uint64_t)(pass * kKBSteps + c * 4) * kBStep;
+            if (c < 5) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, (c | j) != 0);
+              for (int j = 0; j < 4; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, (c | j) != 0);
             } else {
 #pragma unroll
-              for (int j = 0; j < 6; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, 1);
+              for (int j = 0; j < 2; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, 1);
             }
             mma_commit<2>(&aempty[slot]);             // A slot reusable once these MMAs have read it
           }
