@@ -44,7 +44,7 @@ constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 32;   // TMEM columns: D0 | D
 
 struct AnaTcParams {
   Geo g;
-  const float* rin;     // (N,1,Fd,Fh,Fw) residual (or yp for iteration 0)
+  const float* rin;     // (N,1,Fd,Fh,Fw) residual (or yp for iteration 0), ALREADY rounded to tf32 (k_round_tf32)
   float* z;             // internal code layout: channels-last (N,Qd,Qh,Qw,176), updated in place
   const float* wpack;   // this layer: [2 ranks][43 k-steps][11 groups][2][8][4] tf32-rounded filters
   const float* t0;      // [M]
@@ -70,6 +70,17 @@ __global__ void k_pack_tc_analysis(const float* __restrict__ w, float* __restric
     int m = rank * kNAH + grp * 8 + r8, j = kc * 4 + e;              // k-step ks = (td,th) row; column j: 0 = pad, 1..7 = tw 0..6
     float v = (m < M && j > 0) ? w[(size_t)m * kTaps + ks * 7 + (j - 1)] : 0.0f;
     out[i] = ptx::to_tf32_rna(v);
+  }
+}
+
+// r -> tf32 (RNE) once per element, before the analysis: every element is used by ~43 windows and the tensor core
+// would truncate.  Image-sized stream (4 MB per 16x256x256 clip), negligible next to the code traffic.
+__global__ void __launch_bounds__(256) k_round_tf32(const float* __restrict__ src, float* __restrict__ dst, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    v.x = __uint_as_float(ptx::tf32_rna_bits(v.x)); v.y = __uint_as_float(ptx::tf32_rna_bits(v.y));
+    v.z = __uint_as_float(ptx::tf32_rna_bits(v.z)); v.w = __uint_as_float(ptx::tf32_rna_bits(v.w));
+    reinterpret_cast<float4*>(dst)[i] = v;
   }
 }
 
@@ -146,19 +157,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
       const int buf = it & 1;
       CDL_TW(tw1, mbar_wait(&rfull[buf], (it >> 1) & 1); named_bar_sync(1, 128));   // tile `it` landed; everyone left tile it-1
       if (tid == 0 && tile + npairs < p.ntiles) issue_tile_load(tile + npairs, buf ^ 1);
-      // round the tile to tf32 (RNE) once, in place: every element is used by ~43 windows, and the tensor core would
-      // truncate.  After this the im2col expansion is pure data movement.
-      {
-        float4* t4 = reinterpret_cast<float4*>(sR + buf * kRTilePad);
-        for (int i = tid; i < kRTile / 4; i += 128) {
-          float4 v = t4[i];
-          v.x = __uint_as_float(tf32_rna_bits(v.x)); v.y = __uint_as_float(tf32_rna_bits(v.y));
-          v.z = __uint_as_float(tf32_rna_bits(v.z)); v.w = __uint_as_float(tf32_rna_bits(v.w));
-          t4[i] = v;
-        }
-        fence_async_smem();                       // generic-proxy writes ordered before the TMA that later refills this buffer
-        named_bar_sync(1, 128);
-      }
       // this thread's coarse site: row `warp` of the CTA tile, column `lane`
       const float* rs = sR + buf * kRTilePad + (2 * warp) * kRW + 2 * lane;
 #pragma unroll
@@ -287,7 +285,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
     __syncwarp();                                   // reconverge the MMA warp before the aligned cluster barrier
   }
   if (p.dbg && lane == 0) {
-    long long* d = p.dbg + ((size_t)blockIdx.x * 16 + warp) * 8;
+    long long* d = p.dbg + ((size_t)blockIdx.x * 24 + warp) * 8;
     d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2; d[4] = tw3; d[5] = tw4; d[6] = tw5;
   }
   // teardown: everyone done (all MMAs were consumed by the epilogues before they exit)

@@ -24,14 +24,14 @@ for k in range(1, 4):
     plan.analysis_step(k, r, z, c)
 torch.cuda.synchronize()
 lib = cb.load_library()
-dbg = torch.zeros(148 * 16 * 8, dtype=torch.int64, device=d)
+dbg = torch.zeros(148 * 24 * 8, dtype=torch.int64, device=d)
 lib.cdl__debug_set_buffer.argtypes = [ctypes.c_void_p]
 lib.cdl__debug_set_buffer(ctypes.c_void_p(dbg.data_ptr()))
 
 
 def show(name, roles):
     torch.cuda.synchronize()
-    t = dbg.view(148, 16, 8).cpu().double()
+    t = dbg.view(148, 24, 8).cpu().double()
     print(f"== {name}: cycles (mean over CTAs; rank0 = even blocks)")
     for rname, warps, labels in roles:
         for rk in (0, 1):
@@ -45,7 +45,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); plan.synthesis_step(4, z, r, yp, None, residual=True); e1.record()
 show("synthesis", [("producer", list(range(0, 8)), ["wait aempty", "wait xfull", "cvt(+ld wait)", "request", "st+arrive", "flush total"]),
                    ("epilogue", list(range(8, 12)), ["wait dfull", "flush+bars", "-"]),
-                   ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
+                   ("mma", [12], ["wait dempty", "wait afull", "wait weights"]), ("flush", [13, 14, 15, 16], ["-", "wait xfull", "-"])])
 print("   launch ms", e0.elapsed_time(e1))
 e0.record(); plan.analysis_step(4, r, z, c); e1.record()
 show("analysis", [("producer", list(range(0, 4)), ["wait aempty", "wait r tile", "wait::st", "tmem_st issue", "fence+arrive", "round pass"]),
