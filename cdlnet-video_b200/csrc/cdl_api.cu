@@ -635,18 +635,18 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.a_lo = 0;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
-    tc::k_tc_synthesis<<<2 * pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a);
+    tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
     CDL_LAUNCH_CHECK(p);
     if (!residual && k == 0) {
       // Final dictionary synthesis xphat = D z (model/net.py:90,210): its tf32 rounding lands directly on xhat and
       // dominates the output error (measured: 7e-5 of 8e-5), so the two dropped cross terms are added back:
       //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)       (the scatter-add accumulates the three launches)
       a.a_lo = 1;
-      tc::k_tc_synthesis<<<2 * pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a);
+      tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
       CDL_LAUNCH_CHECK(p);
       a.a_lo = 0;
       a.wpack = p->wBtc_lo;
-      tc::k_tc_synthesis<<<2 * pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a);
+      tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
       CDL_LAUNCH_CHECK(p);
     }
     return CDL_OK;

@@ -38,7 +38,6 @@ constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 32;   // TMEM: D0 | D1 | 
 constexpr int kASlotsB = 4;               // A ring depth (32 subbands = 4 K-steps per slot; 6 chunks per pass)
 constexpr int kXD = 7, kXH = 13, kXW = 72;                   // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
 constexpr int kXTile = kXD * kXH * kXW;
-constexpr int kSynThreads = kThreads + 128;               // + 4 flush warps (13..16)
 
 struct SynTcParams {
   Geo g;
@@ -194,7 +193,7 @@ __device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int 
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc_synthesis(const SynTcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_synthesis(const SynTcParams p) {
   using namespace ptx;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* sB = reinterpret_cast<float*>(smem_raw);
@@ -220,13 +219,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 4); mbar_init(&xfree[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 4); mbar_init(&xfree[i], 8); }
     for (int i = 0; i < kASlotsB; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
-  for (int i = tid; i < 2 * kXTile; i += kSynThreads) sX[i] = 0.0f;
+  for (int i = tid; i < 2 * kXTile; i += kThreads) sX[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(wbar, (uint32_t)kSynSmemB);
@@ -244,14 +243,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
     // warp = 4*half + quad: TMEM lanes of tile row `quad`; `half` selects which half of every K-chunk this warp converts
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
-    int it = 0;
-    uint32_t gch = 0;
-    float rg[6][16];
+    // out[fine] += footprint of tile `t` (the j-th tile of this CTA), then clear the buffer for tile j+2
+    auto flush_tile = [&](int t, int j) {
+      const int xb = j & 1;
+      CDL_TW(tw1, mbar_wait(&xfull[xb], (j >> 1) & 1));
+      int n, qd, qh0, qw0;
+      syn_tile_coords(p, t, n, qd, qh0, qw0);
+      qh0 += rank * kTH;
+      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;
+      float* on = p.out + (size_t)n * g.fine_vol();
+      float* xs = sX + xb * kXTile;
+      for (int r = warp; r < kXD * kXH; r += 8) {                // one 72-float row per warp pass, 18 float4 per row
+        const int h = r % kXH, d = r / kXH;
+        const int gd = fd0 + d, gh = fh0 + h, gw = fw0 + 4 * lane;
+        if (lane < kXW / 4) {
+          float4* cell = reinterpret_cast<float4*>(xs + r * kXW + 4 * lane);
+          const float4 v = *cell;
+          *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh && gw >= 0 && gw + 4 <= g.Fw)
+            red_add_v4_f32(on + ((size_t)gd * g.Fh + gh) * g.Fw + gw, v);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfree[xb]);
+    };
     const int a_lo = p.a_lo;
-    auto cvt_a = [a_lo](float x) {                               // hi part, or the part tf32 rounding drops (3-term D z)
+    auto cvt_a = [a_lo](float x) {
       const float hi = __uint_as_float(tf32_rna_bits(x));
       return a_lo ? __uint_as_float(tf32_rna_bits(x - hi)) : hi;
     };
+    int it = 0;
+    uint32_t gch = 0;
+    float rg[6][16];
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
       int n, qd, qh0, qw0;
       syn_tile_coords(p, tile, n, qd, qh0, qw0);
@@ -307,7 +330,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
         CDL_TW(tw4, tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
         if (pc >= 6) load_group(rg[c], zs2, c, valid2);          // group is dead for this tile: refill it for the next one
       }
+      CDL_TW(tw5, if (it > 0) flush_tile(tile - npairs, it - 1));
     }
+    if (it > 0) flush_tile(pair + (it - 1) * npairs, it - 1);      // footprint of the last tile
   } else if (warp < kMmaWarp) {
     // ============================== epilogue: col2im ==============================
     const int ew = warp - 8;
@@ -324,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
       if (lane == 0) mbar_arrive(&xfull[xb]);      // this warp's rows are in; 4 arrivals -> producers flush the tile
       named_bar_sync(2, 128);                      // th lock step restarts with everyone at group 0
     }
-  } else if (warp == kMmaWarp) {
+  } else {
     // ============================== MMA issue (leader CTA, one thread) ==============================
     if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0 && lane == 0) {
@@ -359,34 +384,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
       }
     }
     __syncwarp();
-  } else {
-    // ============================== flush warps (13..16): footprint tile -> out ==============================
-    const int fw = warp - (kMmaWarp + 1);
-    int j = 0;
-    for (int t = pair; t < p.ntiles; t += npairs, ++j) {
-      // out[fine] += footprint of tile t, then clear the buffer for tile j+2 (red.global.add.v4: tiles overlap)
-      const int xb = j & 1;
-      CDL_TW(tw1, mbar_wait(&xfull[xb], (j >> 1) & 1));
-      int n, qd, qh0, qw0;
-      syn_tile_coords(p, t, n, qd, qh0, qw0);
-      qh0 += rank * kTH;
-      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;
-      float* on = p.out + (size_t)n * g.fine_vol();
-      float* xs = sX + xb * kXTile;
-      for (int r = fw; r < kXD * kXH; r += 4) {                  // one 72-float row per warp pass, 18 float4 per row
-        const int h = r % kXH, d = r / kXH;
-        const int gd = fd0 + d, gh = fh0 + h, gw = fw0 + 4 * lane;
-        if (lane < kXW / 4) {
-          float4* cell = reinterpret_cast<float4*>(xs + r * kXW + 4 * lane);
-          const float4 v = *cell;
-          *cell = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh && gw >= 0 && gw + 4 <= g.Fw)
-            red_add_v4_f32(on + ((size_t)gd * g.Fh + gh) * g.Fw + gw, v);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xfree[xb]);
-    }
   }
   if (p.dbg && lane == 0) {
     long long* d = p.dbg + ((size_t)blockIdx.x * 24 + warp) * 8;

@@ -45,7 +45,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); plan.synthesis_step(4, z, r, yp, None, residual=True); e1.record()
 show("synthesis", [("producer", list(range(0, 8)), ["wait aempty", "wait xfull", "cvt(+ld wait)", "request", "st+arrive", "flush total"]),
                    ("epilogue", list(range(8, 12)), ["wait dfull", "flush+bars", "-"]),
-                   ("mma", [12], ["wait dempty", "wait afull", "wait weights"]), ("flush", [13, 14, 15, 16], ["-", "wait xfull", "-"])])
+                   ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
 print("   launch ms", e0.elapsed_time(e1))
 e0.record(); plan.analysis_step(4, r, z, c); e1.record()
 show("analysis", [("producer", list(range(0, 4)), ["wait aempty", "wait r tile", "wait::st", "tmem_st issue", "fence+arrive", "round pass"]),
