@@ -635,6 +635,17 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.a_lo = 0;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
+    {
+      // Units: (n, d-segment, h-tile, w-tile) columns of `seg` consecutive coarse frames; seg is the largest divisor
+      // of Qd that still leaves >= 4 units per CTA pair (load balance), because only the last tile of a unit flushes
+      // its whole 7-plane footprint.
+      const int cols = p->g.N * a.tiles_h * a.tiles_w;
+      int seg = 1;
+      for (int d = 1; d <= p->g.Qd; ++d)
+        if (p->g.Qd % d == 0 && (long long)cols * (p->g.Qd / d) >= 4LL * pairs) seg = d;
+      a.seg = seg; a.nseg = p->g.Qd / seg; a.nunits = cols * a.nseg;
+      if (pairs > a.nunits) pairs = a.nunits;
+    }
     tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
     CDL_LAUNCH_CHECK(p);
     if (!residual && k == 0) {

@@ -20,8 +20,10 @@
 //     by warp shuffles (-> the 2 fine voxels of its own cell, plus 5 spill voxels per warp), then adds a
 //     float2 to the CTA's fine tile in shared memory.  Warps (= h-rows of the tile) proceed in lock step
 //     over th (named barrier between th groups), so no two warps ever touch the same row: no shared-memory
-//     atomics.  The finished 7 x 13 x 69 footprint is handed to the producer warps, which add it to `out`
-//     with red.global.add.v4.f32 (tiles overlap) while the col2im warps start the next tile.
+//     atomics.  A CTA pair sweeps consecutive coarse frames of one column, so the footprints of successive tiles
+//     overlap in d inside shared memory (a ring of 9 fine planes): after each tile only the 2 planes that are final
+//     are handed to the producer warps, which add them to `out` with red.global.add.v4.f32 (3.5x fewer global
+//     reductions than flushing every 7-plane footprint) while the col2im warps start the next tile.
 #pragma once
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
@@ -37,7 +39,8 @@ constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in pass 0 (p
 constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 32;   // TMEM: D0 | D1 | A0..A3  (480 of 512)
 constexpr int kASlotsB = 4;               // A ring depth (32 subbands = 4 K-steps per slot; 6 chunks per pass)
 constexpr int kXD = 7, kXH = 13, kXW = 72;                   // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
-constexpr int kXTile = kXD * kXH * kXW;
+constexpr int kXPlanes = 9;                                  // ring of fine d-planes: 7 being accumulated + 2 being flushed
+constexpr int kXTile = kXPlanes * kXH * kXW;
 
 struct SynTcParams {
   Geo g;
@@ -45,12 +48,13 @@ struct SynTcParams {
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
   const float* wpack;   // this layer: [2 ranks][2 passes][22 k-steps][11 groups][2][8][4]
   int tiles_w, tiles_h, ntiles;
+  int seg, nseg, nunits; // a CTA pair sweeps `seg` consecutive coarse frames of one (n, h-tile, w-tile) column per unit
   int a_lo;             // 0: A = rna_tf32(z) ; 1: A = rna_tf32(z - rna_tf32(z))  (low part, used by the 3-term final synthesis)
   long long* dbg;
 };
 
 constexpr size_t kSynSmemB = (size_t)2 * kKBSteps * (kNBP / 2) * 8 * sizeof(float);             // 123904
-constexpr size_t kSynSmemX = 2 * (size_t)kXTile * sizeof(float);                                // two footprint tiles, 52416
+constexpr size_t kSynSmemX = (size_t)kXTile * sizeof(float);                                    // 9-plane footprint ring, 33696
 constexpr size_t kSynSmemBytes = kSynSmemB + kSynSmemX + 256;
 
 // filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[pass][n = 7*row + tw, k = m], per-rank UMMA layout, tf32 RNE.
@@ -92,7 +96,7 @@ struct EdgeMasks { float lt31, lt30, gt0; };   // 1.0 / 0.0 lane masks: fma(x, m
 // Phase 1: w-direction reduction with shuffles (independent across rows), phase 2: all shared-memory loads,
 // phase 3: adds and stores - so the NR read-modify-writes overlap instead of forming one dependent chain.
 template <int R0, int NR, int RC0, int COLS>
-__device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs, int hrow, int lane, const EdgeMasks& em) {
+__device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs, int pbase, int hrow, int lane, const EdgeMasks& em) {
   constexpr int th = R0 / 7;
   const unsigned full = 0xffffffffu;
   float x0[NR], x1[NR], e1[NR], e2[NR], e3[NR], f5[NR], f6[NR];
@@ -114,7 +118,8 @@ __device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs,
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     const int td = (R0 + i) % 7;
-    rowp[i] = xs + (td * kXH + 2 * hrow + th) * kXW;
+    const int ps = pbase + td - ((pbase + td >= kXPlanes) ? kXPlanes : 0);          // ring slot of fine plane 2*qd + td
+    rowp[i] = xs + (ps * kXH + 2 * hrow + th) * kXW;
     cur[i] = *reinterpret_cast<const float2*>(rowp[i] + 4 + 2 * lane);
   }
 #pragma unroll
@@ -147,25 +152,33 @@ __device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs,
 // rows [R, REND) whose first row RC0 sits at u[0], split at th-group boundaries; warps run the th groups in lock
 // step (named barrier 2) so that no two warps ever touch the same shared-memory row at the same time
 template <int R, int REND, int RC0, int COLS>
-__device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, int hrow, int lane, const EdgeMasks& em) {
+__device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, int pbase, int hrow, int lane, const EdgeMasks& em) {
   if constexpr (R < REND) {
     constexpr int RB = ((R / 7) + 1) * 7 < REND ? ((R / 7) + 1) * 7 : REND;
     if constexpr (R % 7 == 0 && R > 0) ptx::named_bar_sync(2, 128);
-    rows_apply<R, RB - R, RC0, COLS>(u, xs, hrow, lane, em);
-    rows_walk<RB, REND, RC0, COLS>(u, xs, hrow, lane, em);
+    rows_apply<R, RB - R, RC0, COLS>(u, xs, pbase, hrow, lane, em);
+    rows_walk<RB, REND, RC0, COLS>(u, xs, pbase, hrow, lane, em);
   }
 }
 
-__device__ __forceinline__ void syn_tile_coords(const SynTcParams& p, int tile, int& n, int& qd, int& qh0, int& qw0) {
-  int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  int th = tile % p.tiles_h; tile /= p.tiles_h;
-  qd = tile % p.g.Qd; n = tile / p.g.Qd;
-  qh0 = th * 2 * kTH; qw0 = tw * kTW;
+struct SynTile { int n, qd, qh0, qw0, first, last; };
+// j-th tile of CTA pair `pair`: unit u = pair + (j / seg) * npairs is a (n, d-segment, h-tile, w-tile) column of `seg`
+// consecutive coarse frames, swept in order of qd
+__device__ __forceinline__ SynTile syn_tile(const SynTcParams& p, int pair, int npairs, int j) {
+  int u = pair + (j / p.seg) * npairs;
+  const int k = j % p.seg;
+  SynTile t;
+  t.qw0 = (u % p.tiles_w) * kTW; u /= p.tiles_w;
+  t.qh0 = (u % p.tiles_h) * 2 * kTH; u /= p.tiles_h;
+  t.qd = (u % p.nseg) * p.seg + k;
+  t.n = u / p.nseg;
+  t.first = k == 0; t.last = k == p.seg - 1;
+  return t;
 }
 
 // one accumulator pass (176 columns = rows [RFIRST, RLAST) of 7 taps) drained in three 64-column loads of 9/9/rest rows
 template <int RFIRST, int RLAST>
-__device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int hrow, int lane, const EdgeMasks& em,
+__device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int pbase, int hrow, int lane, const EdgeMasks& em,
                                                   uint64_t* dempty_p, uint64_t* dfull_p, uint32_t parity, long long& tw, uint32_t rank) {
   using namespace ptx;
   CDL_TW(tw, mbar_wait(dfull_p, parity));
@@ -174,13 +187,13 @@ __device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int 
     uint32_t u[64];
     tmem_ld64(dcol, u);
     tmem_wait_ld();
-    rows_walk<RFIRST, RFIRST + 9, RFIRST, 64>(u, xs, hrow, lane, em);
+    rows_walk<RFIRST, RFIRST + 9, RFIRST, 64>(u, xs, pbase, hrow, lane, em);
   }
   {
     uint32_t u[64];
     tmem_ld64(dcol + 63, u);
     tmem_wait_ld();
-    rows_walk<RFIRST + 9, RFIRST + 18, RFIRST + 9, 64>(u, xs, hrow, lane, em);
+    rows_walk<RFIRST + 9, RFIRST + 18, RFIRST + 9, 64>(u, xs, pbase, hrow, lane, em);
   }
   {
     uint32_t u[64];
@@ -189,7 +202,7 @@ __device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) { if (rank == 0) mbar_arrive(dempty_p); else mbar_arrive_cluster(dempty_p, 0); }   // accumulator free again
-    rows_walk<RFIRST + 18, RLAST, RFIRST + 18, 64>(u, xs, hrow, lane, em);
+    rows_walk<RFIRST + 18, RLAST, RFIRST + 18, 64>(u, xs, pbase, hrow, lane, em);
   }
 }
 
@@ -225,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
-  for (int i = tid; i < 2 * kXTile; i += kThreads) sX[i] = 0.0f;
+  for (int i = tid; i < kXTile; i += kThreads) sX[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(wbar, (uint32_t)kSynSmemB);
@@ -237,27 +250,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   cluster_sync_all();          // barriers initialised, TMEM allocated (filters may still be in flight)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
+  const int my_tiles = (pair < p.nunits) ? ((p.nunits - pair + npairs - 1) / npairs) * p.seg : 0;
 
   if (warp < 8) {
     // ============================== producers: code tile -> tf32 -> TMEM A ring; footprint flush ==============================
     // warp = 4*half + quad: TMEM lanes of tile row `quad`; `half` selects which half of every K-chunk this warp converts
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
-    // out[fine] += footprint of tile `t` (the j-th tile of this CTA), then clear the buffer for tile j+2
-    auto flush_tile = [&](int t, int j) {
-      const int xb = j & 1;
-      CDL_TW(tw1, mbar_wait(&xfull[xb], (j >> 1) & 1));
-      int n, qd, qh0, qw0;
-      syn_tile_coords(p, t, n, qd, qh0, qw0);
-      qh0 += rank * kTH;
-      const int fd0 = 2 * qd - g.od, fh0 = 2 * qh0 - 3, fw0 = 2 * qw0 - 4;
-      float* on = p.out + (size_t)n * g.fine_vol();
-      float* xs = sX + xb * kXTile;
-      for (int r = warp; r < kXD * kXH; r += 8) {                // one 72-float row per warp pass, 18 float4 per row
-        const int h = r % kXH, d = r / kXH;
-        const int gd = fd0 + d, gh = fh0 + h, gw = fw0 + 4 * lane;
+    // After tile j (coarse frame qd) the fine planes 2*qd-od and 2*qd-od+1 are final (all 7 of the footprint at the end
+    // of a unit): out[fine] += plane, then clear its ring slot.
+    auto flush_tile = [&](int j) {
+      const SynTile t = syn_tile(p, pair, npairs, j);
+      CDL_TW(tw1, mbar_wait(&xfull[j & 1], (j >> 1) & 1));
+      const int fh0 = 2 * (t.qh0 + (int)rank * kTH) - 3, fw0 = 2 * t.qw0 - 4;
+      float* on = p.out + (size_t)t.n * g.fine_vol();
+      const int nrows = (t.last ? kXD : 2) * kXH;
+      for (int r = warp; r < nrows; r += 8) {                    // one 72-float row per warp pass, 18 float4 per row
+        const int h = r % kXH, pi = r / kXH;
+        const int pr = 2 * t.qd + pi;                            // plane index along the sweep; fine d = pr - od
+        const int gd = pr - g.od, gh = fh0 + h, gw = fw0 + 4 * lane;
         if (lane < kXW / 4) {
-          float4* cell = reinterpret_cast<float4*>(xs + r * kXW + 4 * lane);
+          float4* cell = reinterpret_cast<float4*>(sX + ((pr % kXPlanes) * kXH + h) * kXW + 4 * lane);
           const float4 v = *cell;
           *cell = make_float4(0.f, 0.f, 0.f, 0.f);
           if (gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh && gw >= 0 && gw + 4 <= g.Fw)
@@ -265,7 +278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&xfree[xb]);
+      if (lane == 0) mbar_arrive(&xfree[j & 1]);
     };
     const int a_lo = p.a_lo;
     auto cvt_a = [a_lo](float x) {
@@ -275,19 +288,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     int it = 0;
     uint32_t gch = 0;
     float rg[6][16];
-    for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
-      int n, qd, qh0, qw0;
-      syn_tile_coords(p, tile, n, qd, qh0, qw0);
-      const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
+    for (; it < my_tiles; ++it) {
+      const SynTile t = syn_tile(p, pair, npairs, it);
+      const SynTile t2 = syn_tile(p, pair, npairs, it + 1 < my_tiles ? it + 1 : it);
+      const int qh = t.qh0 + rank * kTH + quad, qw = t.qw0 + lane;
       const int valid = qh < g.Qh && qw < g.Qw;
-      const float* zs = p.z + ((((size_t)n * g.Qd + qd) * g.Qh + qh) * g.Qw + qw) * kKB;
-      if (half == 0 && lane == 0 && tile + npairs < p.ntiles) {  // next tile: this row's 32 sites x 704 B are contiguous
-        int n2, qd2, qh02, qw02;
-        syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + quad;
+      const float* zs = p.z + ((((size_t)t.n * g.Qd + t.qd) * g.Qh + qh) * g.Qw + qw) * kKB;
+      if (half == 0 && lane == 0 && it + 1 < my_tiles) {         // next tile: this row's 32 sites x 704 B are contiguous
+        const int qh2 = t2.qh0 + rank * kTH + quad;
         if (qh2 < g.Qh) {
-          const int nq = min(kTW, g.Qw - qw02);
-          bulk_prefetch_l2(p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw02) * kKB, (uint32_t)nq * kKB * 4);
+          const int nq = min(kTW, g.Qw - t2.qw0);
+          bulk_prefetch_l2(p.z + ((((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2) * g.Qw + t2.qw0) * kKB, (uint32_t)nq * kKB * 4);
         }
       }
       // This thread's 88 subbands (its half of the six 32-subband K-chunks: 5 x 16 + 8) live in registers for the whole
@@ -307,12 +318,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       }
       const float* zs2 = zs;                                     // the next tile's site (for the register refill)
       int valid2 = 0;
-      if (tile + npairs < p.ntiles) {
-        int n2, qd2, qh02, qw02;
-        syn_tile_coords(p, tile + npairs, n2, qd2, qh02, qw02);
-        const int qh2 = qh02 + rank * kTH + quad, qw2 = qw02 + lane;
+      if (it + 1 < my_tiles) {
+        const int qh2 = t2.qh0 + rank * kTH + quad, qw2 = t2.qw0 + lane;
         valid2 = qh2 < g.Qh && qw2 < g.Qw;
-        zs2 = p.z + ((((size_t)n2 * g.Qd + qd2) * g.Qh + qh2) * g.Qw + qw2) * kKB;
+        zs2 = p.z + ((((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2) * g.Qw + qw2) * kKB;
       }
 #pragma unroll
       for (int pc = 0; pc < 12; ++pc, ++gch) {                   // 2 passes x 6 K-chunks of 32 subbands (the last holds 16)
@@ -330,23 +339,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
         CDL_TW(tw4, tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
         if (pc >= 6) load_group(rg[c], zs2, c, valid2);          // group is dead for this tile: refill it for the next one
       }
-      CDL_TW(tw5, if (it > 0) flush_tile(tile - npairs, it - 1));
+      CDL_TW(tw5, if (it > 0) flush_tile(it - 1));
     }
-    if (it > 0) flush_tile(pair + (it - 1) * npairs, it - 1);      // footprint of the last tile
+    if (it > 0) flush_tile(it - 1);                                // planes of the last tile
   } else if (warp < kMmaWarp) {
     // ============================== epilogue: col2im ==============================
     const int ew = warp - 8;
     const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
     const EdgeMasks em = {lane < 31 ? 1.0f : 0.0f, lane < 30 ? 1.0f : 0.0f, lane > 0 ? 1.0f : 0.0f};
-    int it = 0;
-    for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+    for (int it = 0; it < my_tiles; ++it) {
+      const SynTile t = syn_tile(p, pair, npairs, it);
       const int xb = it & 1;
-      float* xs = sX + xb * kXTile;
-      CDL_TW(tw1, mbar_wait(&xfree[xb], ((it >> 1) & 1) ^ 1));      // footprint buffer flushed + cleared (first two uses pass)
-      syn_epilogue_pass<0, kRowsP0>(lane_addr + kColDB, xs, ew, lane, em, &dempty[0], &dfull[0], it & 1, tw0, rank);
-      syn_epilogue_pass<kRowsP0, 49>(lane_addr + kColDB + kNBP, xs, ew, lane, em, &dempty[1], &dfull[1], it & 1, tw0, rank);
+      // the two planes this tile opens (2*qd+5, 2*qd+6) reuse the ring slots flushed after tile it-2 ...
+      CDL_TW(tw1, mbar_wait(&xfree[xb], ((it >> 1) & 1) ^ 1));
+      // ... and a new unit may start anywhere in the ring: wait for the complete flush that ended the previous unit
+      if (t.first && it > 0) CDL_TW(tw1, mbar_wait(&xfree[(it - 1) & 1], ((it - 1) >> 1) & 1));
+      const int pbase = (2 * t.qd) % kXPlanes;
+      syn_epilogue_pass<0, kRowsP0>(lane_addr + kColDB, sX, pbase, ew, lane, em, &dempty[0], &dfull[0], it & 1, tw0, rank);
+      syn_epilogue_pass<kRowsP0, 49>(lane_addr + kColDB + kNBP, sX, pbase, ew, lane, em, &dempty[1], &dfull[1], it & 1, tw0, rank);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&xfull[xb]);      // this warp's rows are in; 4 arrivals -> producers flush the tile
+      if (lane == 0) mbar_arrive(&xfull[xb]);      // this warp's rows are in; 4 arrivals -> producers flush the final planes
       named_bar_sync(2, 128);                      // th lock step restarts with everyone at group 0
     }
   } else {
@@ -359,7 +371,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       const uint32_t idesc = make_idesc_tf32(256, kNBP);
       int it = 0;
       uint32_t gch = 0;
-      for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
+      for (; it < my_tiles; ++it) {
         for (int pass = 0; pass < 2; ++pass) {
           CDL_TW(tw0, mbar_wait_cluster(&dempty[pass], (it & 1) ^ 1));
           tc_fence_after();
