@@ -59,7 +59,8 @@ def build(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libcdl_b200.so")
     tmp = LIB_PATH + ".tmp%d" % os.getpid()
-    cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-o", tmp, *sources()]
+    extra = ["-DCDL_TC_PROFILE"] if os.environ.get("CDL_TC_PROFILE") else []      # per-role cycle counters (dev aid)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-o", tmp, *sources()]
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
