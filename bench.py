@@ -33,7 +33,7 @@ L_SPECTRAL = 1.375e4                            # reference test.ipynb:171, powe
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step")
@@ -116,7 +116,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -305,7 +305,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = te.item() / args.steps
     e2e_value = world * n_clips * alg["V"] / (e2e_ms * 1e-3) / 1e6
-    e2e_ok = float((x_host.to(dev) - xhat).abs().max()) <= 1e-5      # red.add order makes runs differ by ~1e-7
+    e2e_diff = float((x_host.to(dev) - xhat).abs().max())     # scatter-add order: runs differ at the 1e-5 level (both within 1e-4 of the oracle)
 
     # ---- per-kernel breakdown (CUDA events on the launch stream) -> roofline of the dominant kernel ----
     roof = None
@@ -341,9 +341,16 @@ def main():
         tflops = alg["conv_flops"] / (avg_ms * 1e-3) / 1e12
         gbs = 2 * alg["z_pass"] / (avg_ms * 1e-3) / 1e9 if dom == "analysis" else alg["z_pass"] / (avg_ms * 1e-3) / 1e9
         tf32_peak = peaks.get("bf16_tflops_sustained", 1400.0) / 2.0
+        traffic = None
+        try:                                     # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if eff == "tf32" and tj.get("clips") == n_clips:
+                traffic = tj[dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"kernel": f"{dom} ({'tcgen05 tf32' if eff == 'tf32' else 'CUDA-core fp32'})", "bound": "tensor",
                 "achieved": tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tflops / tf32_peak,
-                "traffic": None,
+                "traffic": traffic,
                 "peak_source": f"{peak_src}: bf16 sustained / 2 (tf32 is not measured separately; cfg-2 AI 167 FLOP/B is tensor-bound for tf32)",
                 "hbm": {"achieved": gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": gbs / peaks.get("hbm_gbs", 6650.0)},
                 "avg_launch_ms": avg_ms, "launches_per_step": len(tk[dom]),
@@ -365,7 +372,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mvoxels/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(y_host.numel() * 4 + c_host.numel() * 4), "d2h_bytes_per_step": int(x_host.numel() * 4),
-                        "matches_device_path": e2e_ok},
+                        "max_abs_diff_vs_device_path": e2e_diff},
                 "gpu_launches": int(launches),
                 "algorithmic": {"flops_per_step": alg["flops_fwd"], "bytes_per_step": alg["bytes_fwd"],
                                 "tflops": alg["flops_fwd"] / (ms_step * 1e-3) / 1e12, "gbs": alg["bytes_fwd"] / (ms_step * 1e-3) / 1e9}}
