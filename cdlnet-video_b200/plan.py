@@ -133,7 +133,7 @@ class Plan:
     # stepwise API (forward_generator, temporal slabs) ----------------------------------------------
     # The sparse code lives in the plan's internal layout between steps (see include/cdl_b200.h).
     def new_code(self):
-        return torch.zeros(self.code_bytes // 4, dtype=torch.float32, device=self.device)
+        return torch.empty(self.code_bytes // 4, dtype=torch.float32, device=self.device)   # fully written by the first analysis step
 
     def export_code(self, code):
         z = torch.empty(self.z_shape, dtype=torch.float32, device=self.device)
