@@ -294,6 +294,11 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     int nph = next_pow2(cells_h);
     if (THc > nph) THc = nph;
     if (nd3) { while (TWs * THc * TDc * 2 <= kSynThreads && TDc * 2 <= next_pow2(cells_d)) TDc *= 2; }
+    // small problems (one 256x256 image): shrink the tile until there are ~2 CTAs per SM
+    auto n_ctas = [&](int td, int th, int tw) { return (long long)g.N * ceil_div(cells_d, td) * ceil_div(cells_h, th) * ceil_div(strips, tw); };
+    while (n_ctas(TDc, THc, TWs) < 2 * 148 && THc > 2) THc /= 2;
+    while (n_ctas(TDc, THc, TWs) < 2 * 148 && TWs > 4) TWs /= 2;
+    while (n_ctas(TDc, THc, TWs) < 2 * 148 && TDc > 1) TDc /= 2;
     sp.TDc = TDc; sp.THc = THc; sp.TWs = TWs;
     sp.tiles_d = ceil_div(cells_d, TDc); sp.tiles_h = ceil_div(cells_h, THc); sp.tiles_w = ceil_div(strips, TWs);
     auto cdiv_signed = [](int a, int b) { return -floor_div(-a, b); };

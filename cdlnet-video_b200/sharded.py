@@ -98,8 +98,9 @@ class SlabRank:
         self.mean = self.ops.mean_from_sums(sums)
         self.yp = self.ops.center_pad(self.y_loc, self.mean)
         self.c = c
-        self.code = self.ops.new_code()
-        self.r = self.ops.new_fine()
+        if getattr(self, "code", None) is None:          # buffers are allocated once and reused across calls
+            self.code = self.ops.new_code()
+            self.r = self.ops.new_fine()
 
     # -- iterations ----------------------------------------------------------------------------------
     def first(self):
