@@ -577,6 +577,7 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
     a.dbg = g_tc_dbg;
+    a.dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
     if (!ws) return CDL_ERR_WORKSPACE;

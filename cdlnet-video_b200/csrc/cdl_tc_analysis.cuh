@@ -35,12 +35,12 @@ constexpr int kP = 7, kTaps = 343;
 constexpr int kKSteps = 49;              // one tf32 MMA K-step (8 columns) per (td,th) row: window element 0 (zero filter) + 7 taps
 constexpr int kChunkRows = 4;            // (td,th) rows per A chunk -> 32 columns = 4 K-steps
 constexpr int kChunks = 13;              // 12 full chunks + 1 chunk of one row
-constexpr int kASlots = 4;               // A ring depth: covers the producer -> MMA -> producer hand-shake latency
+constexpr int kASlots = 5;               // A ring depth: covers the producer -> MMA -> producer hand-shake latency
 constexpr int kTH = 4, kTW = 32;         // coarse tile per CTA: 1 x 4 x 32 (d,h,w); a pair stacks two along h
 constexpr int kRD = 7, kRH = 2 * (kTH - 1) + kP, kRW = 72;   // residual halo tile (fine): 7 x 13 x 72 floats
 constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats = 26208 B (one TMA box)
 constexpr int kRTilePad = 6560;          // buffer pitch: 26240 B, a multiple of 128 B (TMA destination alignment)
-constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 32;   // TMEM columns: D0 | D1 | A0..A3  (480 of 512)
+constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 32;   // TMEM columns: D0 | D1 | A0..A4  (512 of 512)
 
 struct AnaTcParams {
   Geo g;
@@ -54,6 +54,7 @@ struct AnaTcParams {
   int tiles_w, tiles_h; // pair tiles along w (32 sites) and h (8 rows)
   int ntiles;           // N * Qd * tiles_h * tiles_w
   long long* dbg;       // optional [grid][16 warps][8] cycle counters
+  int dbg_mode;         // development aid: 1 = producers only signal, 2 = epilogue skips the code traffic (results invalid)
 };
 
 constexpr size_t kAnaSmemB = (size_t)kKSteps * kNAH * 8 * sizeof(float);      // 121088
@@ -99,13 +100,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
   float* sT = reinterpret_cast<float*>(smem_raw + kAnaSmemB + kAnaSmemR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kAnaSmemB + kAnaSmemR + kAnaSmemT);
   uint64_t* wbar = bars + 0;
-  uint64_t* afull = bars + 1;    // [4]  (used in the leader CTA) producers of both CTAs -> MMA
-  uint64_t* aempty = bars + 5;   // [4]  MMA commit (multicast) -> producers
-  uint64_t* dfull = bars + 9;    // [2]  MMA commit (multicast) -> epilogue
-  uint64_t* dempty = bars + 11;  // [2]  (leader) epilogue warps of both CTAs -> MMA
-  uint64_t* wready = bars + 13;  //      (leader) the peer CTA's filters have landed
-  uint64_t* rfull = bars + 14;   // [2]  TMA: residual halo tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* afull = bars + 1;                  // [kASlots] (used in the leader CTA) producers of both CTAs -> MMA
+  uint64_t* aempty = afull + kASlots;          // [kASlots] MMA commit (multicast) -> producers
+  uint64_t* dfull = aempty + kASlots;          // [2]  MMA commit (multicast) -> epilogue
+  uint64_t* dempty = dfull + 2;                // [2]  (leader) epilogue warps of both CTAs -> MMA
+  uint64_t* wready = dempty + 2;               //      (leader) the peer CTA's filters have landed
+  uint64_t* rfull = wready + 1;                // [2]  TMA: residual halo tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 2);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,13 +173,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
             const int row = ch * kChunkRows + rr, td = row / kP, th = row % kP;
             const float* src = rs + (td * kRH + th) * kRW;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) lds64(src + 2 * j, raw[8 * rr + 2 * j], raw[8 * rr + 2 * j + 1]);
+            if (!(p.dbg_mode & 1)) { for (int j = 0; j < 4; ++j) lds64(src + 2 * j, raw[8 * rr + 2 * j], raw[8 * rr + 2 * j + 1]); }
           }
         }
         CDL_TW(tw0, mbar_wait(&aempty[slot], ((gchunk / kASlots) & 1) ^ 1));
         tc_fence_after();
         const uint32_t acol = lane_addr + kColA + slot * kASlot;
-        if (ch < kChunks - 1) {
+        if (p.dbg_mode & 1) {
+        } else if (ch < kChunks - 1) {
           tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&raw[0]));
         } else {
           tmem_st8(acol, *reinterpret_cast<const uint32_t(*)[8]>(&raw[0]));
@@ -209,7 +211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         n_tau = n;
       }
       const int qh = qh0 + rank * kTH + quad, qw = qw0 + lane;
-      const int valid = qh < g.Qh && qw < g.Qw;
+      const int valid = qh < g.Qh && qw < g.Qw && !(p.dbg_mode & 2);
       const int ld_ok = valid && !p.first;
       // this site's 88 subbands are contiguous (channels-last): 11 LDG.256 in, 11 STG.256 out
       float* zs = p.z + ((((size_t)n * g.Qd + qd) * g.Qh + qh) * g.Qw + qw) * kNA + m0;

@@ -37,7 +37,7 @@ constexpr int kKBSteps = kKB / 8;         // 22
 constexpr int kNBP = 176;                 // GEMM N per pass
 constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in pass 0 (pass 1: 24)
 constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 32;   // TMEM: D0 | D1 | A0..A3  (480 of 512)
-constexpr int kASlotsB = 4;               // A ring depth (32 subbands = 4 K-steps per slot; 6 chunks per pass)
+constexpr int kASlotsB = 5;               // A ring depth (32 subbands = 4 K-steps per slot; 6 chunks per pass)
 constexpr int kXD = 7, kXH = 13, kXW = 72;                   // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
 constexpr int kXPlanes = 9;                                  // ring of fine d-planes: 7 being accumulated + 2 being flushed
 constexpr int kXTile = kXPlanes * kXH * kXW;
@@ -213,14 +213,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   float* sX = reinterpret_cast<float*>(smem_raw + kSynSmemB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kSynSmemB + kSynSmemX);
   uint64_t* wbar = bars + 0;
-  uint64_t* afull = bars + 1;    // [4] (leader) producers of both CTAs -> MMA
-  uint64_t* aempty = bars + 5;   // [4] MMA commit (multicast) -> producers
-  uint64_t* dfull = bars + 9;    // [2] MMA commit (multicast) -> epilogue   (index = pass)
-  uint64_t* dempty = bars + 11;  // [2] (leader) epilogue warps of both CTAs -> MMA
-  uint64_t* wready = bars + 13;  //     (leader) the peer CTA's filters have landed
-  uint64_t* xfull = bars + 14;   // [2] epilogue -> producers: footprint tile complete, flush it
-  uint64_t* xfree = bars + 16;   // [2] producers -> epilogue: footprint tile flushed and cleared
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* afull = bars + 1;                  // [kASlotsB] (leader) producers of both CTAs -> MMA
+  uint64_t* aempty = afull + kASlotsB;         // [kASlotsB] MMA commit (multicast) -> producers
+  uint64_t* dfull = aempty + kASlotsB;         // [2] MMA commit (multicast) -> epilogue   (index = pass)
+  uint64_t* dempty = dfull + 2;                // [2] (leader) epilogue warps of both CTAs -> MMA
+  uint64_t* wready = dempty + 2;               //     (leader) the peer CTA's filters have landed
+  uint64_t* xfull = wready + 1;                // [2] epilogue -> producers: footprint planes complete, flush them
+  uint64_t* xfree = xfull + 2;                 // [2] producers -> epilogue: planes flushed and cleared
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree + 2);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -16,9 +16,10 @@ using namespace cdl::ptx;
 // B packed per K-step j (8 k-values): [j][n/8][k/4][n%8][k%4]  (SBO = 256 B between 8-row groups, LBO = 128 B between k-chunks)
 // For CG == 2 each CTA holds rows [rank*N/2, (rank+1)*N/2) of B, same packing with N/2 rows.
 template <int CG, bool TS>
-__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K, int rep, long long* cyc) {
+__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K, int rep, long long* cyc, int cgroup) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[8];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0;
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
   float* sA = sB + (size_t)KS * NL * 8;                             // KS * 128 * 8 floats (SS only)
 
   if (warp == 0) { tmem_alloc<CG>(&tmem_base_s, 512); tmem_relinquish<CG>(); }
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&bar2[i], 1); fence_mbar_init(); }
   // B: this CTA's rows
   for (int i = tid; i < KS * NL * 8; i += 128) {
     int j = i / (NL * 8), rem = i % (NL * 8);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
         uint64_t adesc = make_smem_desc_kmajor_noswz(smem_u32(sA) + j * 4096, 128, 256);
         mma_tf32_ss<CG>(tbase, adesc, bdesc, idesc, j > 0);
       }
+      if (cgroup > 0 && (((r * KS + j + 1) & (cgroup - 1)) == 0)) mma_commit<CG>(&bar2[(r + j) & 7]);   // commit every `cgroup` (power of 2) MMAs, nobody waits
     }
     mma_commit<CG>(&bar);
     mbar_wait(&bar, 0);
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
 
 int main(int argc, char** argv) {
   int cg = argc > 1 ? atoi(argv[1]) : 1, ts = argc > 2 ? atoi(argv[2]) : 0, N = argc > 3 ? atoi(argv[3]) : 176, KS = argc > 4 ? atoi(argv[4]) : 7;
-  int rep = argc > 5 ? atoi(argv[5]) : 1, probe = argc > 6 ? atoi(argv[6]) : 0;
+  int rep = argc > 5 ? atoi(argv[5]) : 1, probe = argc > 6 ? atoi(argv[6]) : 0, cgroup = argc > 7 ? atoi(argv[7]) : 0;
   const int M = 128 * cg, K = KS * 8;
   std::vector<float> A((size_t)M * K), B((size_t)N * K), Bp((size_t)N * K), D((size_t)M * N, -1.f), R((size_t)M * N);
   uint32_t s = 12345;
@@ -124,14 +126,14 @@ int main(int argc, char** argv) {
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   long long* dcyc; CK(cudaMalloc(&dcyc, 8)); CK(cudaMemset(dcyc, 0, 8));
-  void (*fn)(const float*, const float*, float*, int, int, int, long long*) =
+  void (*fn)(const float*, const float*, float*, int, int, int, long long*, int) =
       cg == 1 ? (ts ? k_gemm<1, true> : k_gemm<1, false>) : (ts ? k_gemm<2, true> : k_gemm<2, false>);
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K, rep, dcyc));
+  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K, rep, dcyc, cgroup));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   long long hc = 0; CK(cudaMemcpy(&hc, dcyc, 8, cudaMemcpyDeviceToHost));
-  if (rep > 1) printf("timing cg=%d ts=%d N=%d KS=%d rep=%d : %.1f cycles per MMA\n", cg, ts, N, KS, rep, (double)hc / ((double)rep * KS));
+  if (rep > 1) printf("timing cg=%d ts=%d N=%d KS=%d rep=%d commit-every=%d : %.1f cycles per MMA\n", cg, ts, N, KS, rep, cgroup, (double)hc / ((double)rep * KS));
   if (probe) { printf("rounding probe: A = 1 + 0.75*2^-11 (tf32 ulp 2^-10): D[0][0] = %.10f  (1.0 = truncation, 1.0009765625 = round-to-nearest)\n", D[0]); return 0; }
   double maxerr = 0; long bad = 0;
   for (size_t i = 0; i < D.size(); ++i) { double e = fabs((double)D[i] - R[i]); if (e > maxerr) maxerr = e; if (e > 1e-5) ++bad; }
