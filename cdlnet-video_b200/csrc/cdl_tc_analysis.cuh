@@ -33,14 +33,28 @@ constexpr int kNA = 176;                 // GEMM N of the analysis (subbands, pa
 constexpr int kNAH = kNA / 2;            // per-CTA half of the filter bank
 constexpr int kP = 7, kTaps = 343;
 constexpr int kKSteps = 49;              // one tf32 MMA K-step (8 columns) per (td,th) row: window element 0 (zero filter) + 7 taps
-constexpr int kChunkRows = 4;            // (td,th) rows per A chunk -> 32 columns = 4 K-steps
-constexpr int kChunks = 13;              // 12 full chunks + 1 chunk of one row
-constexpr int kASlots = 5;               // A ring depth: covers the producer -> MMA -> producer hand-shake latency
+#ifndef CDL_ANA_ROWS
+#define CDL_ANA_ROWS 7
+#endif
+constexpr int kChunkRows = CDL_ANA_ROWS;                         // (td,th) rows per A chunk = K-steps per chunk (8 columns each)
+constexpr int kChunks = (49 + kChunkRows - 1) / kChunkRows;      // chunks per tile; the last one holds the remaining rows
+constexpr int kRowsLast = 49 - kChunkRows * (kChunks - 1);
+constexpr int kASlots = 160 / (8 * kChunkRows);                  // A ring depth: all TMEM columns left beside the two accumulators
 constexpr int kTH = 4, kTW = 32;         // coarse tile per CTA: 1 x 4 x 32 (d,h,w); a pair stacks two along h
 constexpr int kRD = 7, kRH = 2 * (kTH - 1) + kP, kRW = 72;   // residual halo tile (fine): 7 x 13 x 72 floats
 constexpr int kRTile = kRD * kRH * kRW;  // 6552 floats = 26208 B (one TMA box)
 constexpr int kRTilePad = 6560;          // buffer pitch: 26240 B, a multiple of 128 B (TMA destination alignment)
-constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 32;   // TMEM columns: D0 | D1 | A0..A4  (512 of 512)
+constexpr int kColD = 0, kColA = 2 * kNA, kASlot = 8 * kChunkRows;   // TMEM columns: D0 | D1 | A ring (<= 512)
+static_assert(kASlots >= 2 && kColA + kASlots * kASlot <= 512, "A ring does not fit TMEM");
+
+// store NC (multiple of 8) consecutive TMEM columns from registers
+template <int NC>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const float* v) {
+  using namespace ptx;
+  if constexpr (NC >= 32) { tmem_st32(taddr, *reinterpret_cast<const uint32_t(*)[32]>(v)); tmem_st_cols<NC - 32>(taddr + 32, v + 32); }
+  else if constexpr (NC >= 16) { tmem_st16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(v)); tmem_st_cols<NC - 16>(taddr + 16, v + 16); }
+  else if constexpr (NC >= 8) { tmem_st8(taddr, *reinterpret_cast<const uint32_t(*)[8]>(v)); tmem_st_cols<NC - 8>(taddr + 8, v + 8); }
+}
 
 struct AnaTcParams {
   Geo g;
@@ -165,7 +179,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         const uint32_t slot = gchunk % kASlots;
         // the 8-float window (fine w = 2q-4 .. 2q+3) of each (td,th) row goes to TMEM as is: 8 columns = one K-step
         float raw[8 * kChunkRows];
-        constexpr int kRowsLast = 1;
         const int nrows = (ch < kChunks - 1) ? kChunkRows : kRowsLast;
 #pragma unroll
         for (int rr = 0; rr < kChunkRows; ++rr) {
@@ -181,9 +194,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
         const uint32_t acol = lane_addr + kColA + slot * kASlot;
         if (p.dbg_mode & 1) {
         } else if (ch < kChunks - 1) {
-          tmem_st32(acol, *reinterpret_cast<const uint32_t(*)[32]>(&raw[0]));
+          tmem_st_cols<8 * kChunkRows>(acol, raw);
         } else {
-          tmem_st8(acol, *reinterpret_cast<const uint32_t(*)[8]>(&raw[0]));
+          tmem_st_cols<8 * kRowsLast>(acol, raw);
         }
         CDL_TW(tw2, tmem_wait_st());
         CDL_TW(tw4, tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
@@ -277,7 +290,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_an
 #pragma unroll
             for (int j = 0; j < kChunkRows; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bdesc + (uint64_t)j * kBStep, idesc, (ch | j) != 0);
           } else {
-            mma_tf32_ts<2>(dcol, a0, bdesc, idesc, 1);
+#pragma unroll
+            for (int j = 0; j < kRowsLast; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bdesc + (uint64_t)j * kBStep, idesc, 1);
           }
           mma_commit<2>(&aempty[slot]);             // A slot reusable once these MMAs have read it
         }
