@@ -24,7 +24,7 @@ typedef void (*ana_fn_t)(const AnaParams);
 typedef void (*syn_fn_t)(const SynParams);
 
 struct Offsets {   // byte offsets into the caller's workspace
-  size_t rbuf, partial, sums, yp, mask_p, mean, xphat, code, rtf32, end;
+  size_t rbuf, partial, sums, yp, mask_p, mean, xphat, code, rtf32, rtf32s, end;
   size_t h_y, h_mask, h_c, h_xhat, h_z, h_end;
 };
 
@@ -47,12 +47,16 @@ static int load_encode_tiled() {
   g_encode_tiled = (cdl_encode_tiled_fn)fn;
   return CDL_OK;
 }
-static int make_fine_tmap(CUtensorMap* out, const float* base, const Geo& g) {
-  const cuuint64_t gdim[4] = {(cuuint64_t)g.Fw, (cuuint64_t)g.Fh, (cuuint64_t)g.Fd, (cuuint64_t)g.N};
-  const cuuint64_t gstr[3] = {(cuuint64_t)g.Fw * 4, (cuuint64_t)g.Fw * g.Fh * 4, (cuuint64_t)g.Fw * g.Fh * g.Fd * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)tc::kRW, (cuuint32_t)tc::kRH, (cuuint32_t)tc::kRD, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+static int make_fine_tmap(CUtensorMap* out, const float* base, const Geo& g, int width) {
+  // r viewed as (N, Fd, 2 h-parities, Fh/2, Fw): a box is one h-parity of the analysis halo tile, 36 floats x 19 rows
+  // (every other fine row) x 7 frames; out-of-range coordinates read as zero = the convolution's padding
+  if (g.Fh & 1) return CDL_ERR_UNSUPPORTED;
+  const cuuint64_t W = (cuuint64_t)width;          // row pitch in floats (Fw, or Fw + 4 for the shifted copy)
+  const cuuint64_t gdim[5] = {W, (cuuint64_t)(g.Fh / 2), 2, (cuuint64_t)g.Fd, (cuuint64_t)g.N};
+  const cuuint64_t gstr[4] = {W * 8, W * 4, W * g.Fh * 4, W * g.Fh * g.Fd * 4};
+  const cuuint32_t box[5] = {(cuuint32_t)tc::kARW, (cuuint32_t)tc::kARows, 1, (cuuint32_t)tc::kARD, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CDL_OK : CDL_ERR_UNSUPPORTED;
@@ -259,7 +263,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
 
   p->precision_eff = CDL_PREC_FP32;
   // tensor-core kernels cover the video network of args3d.json: 3D, 7x7x7, stride 2, one channel, M <= 176
-  const bool tc_geom = nd3 && Pd == 7 && Ph == 7 && Pw == 7 && s == 2 && d->C == 1 && d->M <= tc::kNA && (L.fine[2] % 4) == 0 && !d->has_mask;
+  const bool tc_geom = nd3 && Pd == 7 && Ph == 7 && Pw == 7 && s == 2 && d->C == 1 && d->M <= tc::kNA && (L.fine[2] % 4) == 0 && (L.fine[1] % 2) == 0 && !d->has_mask;
   if (d->precision == CDL_PREC_TF32 && tc_geom) { p->tc_ana = true; p->tc_syn = (getenv("CDL_TC_SYN") ? atoi(getenv("CDL_TC_SYN")) != 0 : true); p->precision_eff = CDL_PREC_TF32; }
 
   // ---- CUDA-core analysis configuration ----
@@ -355,7 +359,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     return CDL_CUDA_ERROR_BASE + (int)e;
   }
 
-  p->code_bytes = (p->tc_ana ? (size_t)g.N * g.coarse_vol() * tc::kNA : (size_t)g.N * g.M * g.coarse_vol()) * sizeof(float);
+  p->code_bytes = (p->tc_ana ? tc::code_floats((size_t)g.N * g.Qd * g.Qh, g.Qw) : (size_t)g.N * g.M * g.coarse_vol()) * sizeof(float);
   // ---- workspace layout ----
   {
     Offsets& o = p->off;
@@ -371,7 +375,8 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     o.mean = cur; cur = align_up(cur + (size_t)g.N * sizeof(float), 256);
     o.xphat = cur; cur = align_up(cur + fine_bytes, 256);
     o.code = cur; cur = align_up(cur + p->code_bytes, 256);
-    o.rtf32 = cur; cur = align_up(cur + (p->tc_ana ? fine_bytes : 0), 256);
+    o.rtf32 = cur; cur = align_up(cur + (p->tc_ana ? fine_bytes : 0), 256);                     // tf32(r)
+    o.rtf32s = cur; cur = align_up(cur + (p->tc_ana ? fine_bytes / L.fine[2] * (L.fine[2] + 4) : 0), 256);   // tf32(r), rows shifted by 2 floats
     o.end = cur;
     o.h_y = cur; cur = align_up(cur + in_bytes, 256);
     o.h_mask = cur; cur = align_up(cur + (d->has_mask ? in_bytes : 0), 256);
@@ -426,7 +431,7 @@ extern "C" int cdl_code_export(cdl_plan_t* p, const float* code, float* z, void*
   }
   const long long Q = p->g.coarse_vol();
   dim3 grid((unsigned)((Q + 31) / 32), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
-  tc::k_code_export<<<grid, 256, 0, st>>>(code, z, Q, p->g.M);
+  tc::k_code_export<<<grid, 256, 0, st>>>(code, z, Q, p->g.Qw, p->g.M);
   CDL_LAUNCH_CHECK(p);
   return CDL_OK;
 }
@@ -440,7 +445,7 @@ extern "C" int cdl_code_import(cdl_plan_t* p, const float* z, float* code, void*
   }
   const long long Q = p->g.coarse_vol();
   dim3 grid((unsigned)((Q + 31) / 32), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
-  tc::k_code_import<<<grid, 256, 0, st>>>(z, code, Q, p->g.M);
+  tc::k_code_import<<<grid, 256, 0, st>>>(z, code, Q, p->g.Qw, p->g.M);
   CDL_LAUNCH_CHECK(p);
   return CDL_OK;
 }
@@ -567,14 +572,14 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
   if (p->tc_ana) {
     tc::AnaTcParams a;
     a.g = p->g;
-    a.rin = r; a.z = z;
+    a.z = z;
     a.wpack = p->wAtc + (size_t)k * p->wAtc_layer;
     a.t0 = p->t + (size_t)k * 2 * p->g.M;
     a.t1 = a.t0 + p->g.M;
     a.cvec = c;
     a.first = first ? 1 : 0;
-    a.tiles_w = ceil_div(p->g.Qw, tc::kTW);
-    a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
+    a.tiles_w = ceil_div(p->g.Qw, tc::kATile);
+    a.tiles_h = ceil_div(p->g.Qh, tc::kATile);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
     a.dbg = g_tc_dbg;
     a.dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
@@ -582,16 +587,17 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     if (pairs > a.ntiles) pairs = a.ntiles;
     if (!ws) return CDL_ERR_WORKSPACE;
     float* rr = reinterpret_cast<float*>((char*)ws + p->off.rtf32);
+    float* rs = reinterpret_cast<float*>((char*)ws + p->off.rtf32s);
     {
       const long long n4 = (long long)p->g.N * p->g.fine_vol() / 4;
       long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, n4);
+      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4);
       CDL_LAUNCH_CHECK(p);
     }
-    a.rin = rr;
-    CUtensorMap rmap;
-    { int rc = make_fine_tmap(&rmap, rr, p->g); if (rc) return rc; }
-    tc::k_tc_analysis<<<2 * pairs, tc::kThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a, rmap);
+    CUtensorMap rmap0, rmap1;
+    { int rc = make_fine_tmap(&rmap0, rr, p->g, p->g.Fw); if (rc) return rc; }
+    { int rc = make_fine_tmap(&rmap1, rs, p->g, p->g.Fw + 4); if (rc) return rc; }
+    tc::k_tc_analysis<<<2 * pairs, tc::kAThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a, rmap0, rmap1);
     CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }

@@ -44,7 +44,7 @@ constexpr int kXTile = kXPlanes * kXH * kXW;
 
 struct SynTcParams {
   Geo g;
-  const float* z;       // channels-last code (N,Qd,Qh,Qw,176)
+  const float* z;       // code in the internal quad-blocked layout (code_site_offset)
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
   const float* wpack;   // this layer: [2 ranks][2 passes][22 k-steps][11 groups][2][8][4]
   int tiles_w, tiles_h, ntiles;
@@ -293,23 +293,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       const SynTile t2 = syn_tile(p, pair, npairs, it + 1 < my_tiles ? it + 1 : it);
       const int qh = t.qh0 + rank * kTH + quad, qw = t.qw0 + lane;
       const int valid = qh < g.Qh && qw < g.Qw;
-      const float* zs = p.z + ((((size_t)t.n * g.Qd + t.qd) * g.Qh + qh) * g.Qw + qw) * kKB;
-      if (half == 0 && lane == 0 && it + 1 < my_tiles) {         // next tile: this row's 32 sites x 704 B are contiguous
-        const int qh2 = t2.qh0 + rank * kTH + quad;
-        if (qh2 < g.Qh) {
-          const int nq = min(kTW, g.Qw - t2.qw0);
-          bulk_prefetch_l2(p.z + ((((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2) * g.Qw + t2.qw0) * kKB, (uint32_t)nq * kKB * 4);
+      const float* zs = p.z + code_site_offset(((size_t)t.n * g.Qd + t.qd) * g.Qh + qh, g.Qw, qw);
+      // bulk L2 prefetch two tiles ahead (the register refill below already requests tile it+1 during tile it): one
+      // contiguous 22.5 KB burst per tile row keeps the DRAM reads sequential
+      if (half == 0 && lane == 0) {
+        for (int a = 1; a <= 1; ++a) {
+          if (it + a >= my_tiles) break;
+          const SynTile t3 = syn_tile(p, pair, npairs, it + a);
+          const int qh3 = t3.qh0 + rank * kTH + quad;
+          if (qh3 < g.Qh) {
+            const int nq = (min(kTW, g.Qw - t3.qw0) + 7) & ~7;
+            bulk_prefetch_l2(p.z + code_site_offset(((size_t)t3.n * g.Qd + t3.qd) * g.Qh + qh3, g.Qw, t3.qw0), (uint32_t)nq * kKB * 4);
+          }
         }
       }
       // This thread's 88 subbands (its half of the six 32-subband K-chunks: 5 x 16 + 8) live in registers for the whole
       // tile: converted to tf32 once, stored to TMEM in both passes.  Right after a group's pass-1 store its registers
       // are reloaded with the NEXT tile's values, so every load has several chunk periods to land.
       auto load_group = [&](float (&dst)[16], const float* base, int c, int ok) {
-        if (c < 5) {
-          ldg256_pred(base + 32 * c + 16 * half, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
-          ldg256_pred(base + 32 * c + 16 * half + 8, *reinterpret_cast<float(*)[8]>(&dst[8]), ok);
-        } else {
-          ldg256_pred(base + 160 + 8 * half, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
+        if (c < 5) {                                             // subbands 32c + 16*half + [0,16) = blocks 4c + 2*half, +1
+          ldg256_pred(base + (4 * c + 2 * half) * kCodeBlk, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
+          ldg256_pred(base + (4 * c + 2 * half + 1) * kCodeBlk, *reinterpret_cast<float(*)[8]>(&dst[8]), ok);
+        } else {                                                 // subbands 160 + 8*half + [0,8) = block 20 + half
+          ldg256_pred(base + (20 + half) * kCodeBlk, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
         }
       };
       if (it == 0) {
@@ -321,7 +327,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       if (it + 1 < my_tiles) {
         const int qh2 = t2.qh0 + rank * kTH + quad, qw2 = t2.qw0 + lane;
         valid2 = qh2 < g.Qh && qw2 < g.Qw;
-        zs2 = p.z + ((((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2) * g.Qw + qw2) * kKB;
+        zs2 = p.z + code_site_offset(((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2, g.Qw, qw2);
       }
 #pragma unroll
       for (int pc = 0; pc < 12; ++pc, ++gch) {                   // 2 passes x 6 K-chunks of 32 subbands (the last holds 16)
@@ -363,6 +369,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
     }
   } else {
     // ============================== MMA issue (leader CTA, one thread) ==============================
+    // (the warp-converged issue form of the analysis kernel measured SLOWER here: this kernel is bound by its col2im
+    // warps, and a faster-spinning MMA warp only takes issue slots from the col2im warp it shares a scheduler with)
     if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0 && lane == 0) {
       CDL_TW(tw2, mbar_wait(wbar, 0); mbar_wait_cluster(wready, 0));
@@ -406,16 +414,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
 }
 
-// ---- code layout conversion: internal channels-last (N,Q,176) <-> reference (N,M,Q) ----
-// 32 x 32 tile transpose through shared memory; q and m both coalesced on their respective sides
-__global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ zcl, float* __restrict__ z, long long Q, int M) {
+// ---- code layout conversion: internal quad-blocked channels-last <-> reference (N,M,Qd,Qh,Qw) ----
+// 32 x 32 tile transpose through shared memory; Q = Qd*Qh*Qw sites per sample, R = Qd*Qh rows per sample
+__device__ __forceinline__ size_t code_elem(long long n, long long R, int Qw, long long q, int m) {
+  const long long row = n * R + q / Qw;
+  return code_site_offset((size_t)row, Qw, (int)(q % Qw)) + (size_t)(m >> 3) * kCodeBlk + (m & 7);
+}
+__global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ zcl, float* __restrict__ z, long long Q, int Qw, int M) {
   __shared__ float t[32][33];
   const long long q0 = (long long)blockIdx.x * 32;
   const int m0 = blockIdx.y * 32, n = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
     const long long q = q0 + r; const int m = m0 + tx;
-    t[r][tx] = (q < Q && m < kKB) ? zcl[((long long)n * Q + q) * kKB + m] : 0.0f;
+    t[r][tx] = (q < Q && m < kKB) ? zcl[code_elem(n, Q / Qw, Qw, q, m)] : 0.0f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
@@ -423,7 +435,7 @@ __global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ z
     if (m < M && q < Q) z[((long long)n * M + m) * Q + q] = t[tx][r];
   }
 }
-__global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z, float* __restrict__ zcl, long long Q, int M) {
+__global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z, float* __restrict__ zcl, long long Q, int Qw, int M) {
   __shared__ float t[32][33];
   const long long q0 = (long long)blockIdx.x * 32;
   const int m0 = blockIdx.y * 32, n = blockIdx.z;
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const long long q = q0 + r; const int m = m0 + tx;
-    if (q < Q && m < kKB) zcl[((long long)n * Q + q) * kKB + m] = t[tx][r];
+    if (q < Q && m < kKB) zcl[code_elem(n, Q / Qw, Qw, q, m)] = t[tx][r];
   }
 }
 

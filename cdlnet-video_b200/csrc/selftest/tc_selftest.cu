@@ -16,7 +16,7 @@ using namespace cdl::ptx;
 // B packed per K-step j (8 k-values): [j][n/8][k/4][n%8][k%4]  (SBO = 256 B between 8-row groups, LBO = 128 B between k-chunks)
 // For CG == 2 each CTA holds rows [rank*N/2, (rank+1)*N/2) of B, same packing with N/2 rows.
 template <int CG, bool TS>
-__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K, int rep, long long* cyc, int cgroup) {
+__global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K, int rep, long long* cyc, int cgroup, int ovl) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint64_t bar2[8];
@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
     }
     tmem_wait_st();
   } else {
+    if (ovl) {      // overlapping-window source: A[m][8j+k] = S[rank][j][(m/8)*36 + 4*(m%8) + k]; A carries S in its first floats
+      for (int i = tid; i < KS * 1024; i += 128) sA[i] = A[(size_t)2 * 128 * K + (size_t)rank * KS * 1024 + i];
+    } else
     for (int k = 0; k < K; ++k) {
       int j = k / 8, kk = k % 8;
       sA[(size_t)j * 1024 + (tid / 8) * 64 + (kk / 4) * 32 + (tid % 8) * 4 + (kk % 4)] = A[(size_t)row * K + k];
@@ -60,6 +63,43 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
 
+#ifdef SELFTEST_WARP_ISSUE
+  if (rank == 0 && warp == 0) {      // converged warp, elected lane issues
+#ifdef SELFTEST_CONST
+    if (tbase != 0) __trap();
+    const uint32_t idesc = make_idesc_tf32(128 * CG, 176);
+    const uint64_t bd0 = make_smem_desc_kmajor_noswz(smem_u32(smem), 128, 256);
+    const long long t0 = clock64();
+    for (int r = 0; r < rep; ++r) {
+      if (TS) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          mma_tf32_ts_warp<CG>(0, ACOL + j * 8, bd0 + (uint64_t)((j * (176 / CG) * 32) >> 4), idesc, 1);
+      } else {
+        const uint64_t ad0 = make_smem_desc_kmajor_noswz(smem_u32(smem) + 7 * (176 / CG) * 32, 16, 144);
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          mma_tf32_ss_warp<CG>(0, ad0 + (uint64_t)((j * 4096) >> 4), bd0 + (uint64_t)((j * (176 / CG) * 32) >> 4), idesc, 1);
+      }
+      if (cgroup > 0) mma_commit_warp<CG>(&bar2[r & 7]);
+    }
+#else
+    const uint32_t idesc = make_idesc_tf32(128 * CG, N);
+    const uint64_t bd0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
+    const long long t0 = clock64();
+    for (int r = 0; r < rep; ++r)
+    for (int j = 0; j < KS; ++j) {
+      mma_tf32_ts_warp<CG>(tbase, tbase + ACOL + j * 8, bd0 + (uint64_t)((j * NL * 32) >> 4), idesc, j > 0);
+      if (cgroup > 0 && (((r * KS + j + 1) & (cgroup - 1)) == 0)) mma_commit_warp<CG>(&bar2[(r + j) & 7]);
+    }
+#endif
+    const long long t1 = clock64();
+    mma_commit_warp<CG>(&bar);
+    const long long t2 = clock64();
+    mbar_wait(&bar, 0);
+    if (cyc && tid == 0) { cyc[0] = clock64() - t0; cyc[1] = t1 - t0; cyc[2] = t2 - t1; }
+  }
+#else
   if (rank == 0 && tid == 0) {
     const uint32_t idesc = make_idesc_tf32(128 * CG, N);
     const long long t0 = clock64();
@@ -68,15 +108,18 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
       uint64_t bdesc = make_smem_desc_kmajor_noswz(smem_u32(sB) + j * NL * 32, 128, 256);
       if (TS) mma_tf32_ts<CG>(tbase, tbase + ACOL + j * 8, bdesc, idesc, j > 0);
       else {
-        uint64_t adesc = make_smem_desc_kmajor_noswz(smem_u32(sA) + j * 4096, 128, 256);
+        uint64_t adesc = ovl ? make_smem_desc_kmajor_noswz(smem_u32(sA) + j * 4096, 16, 144) : make_smem_desc_kmajor_noswz(smem_u32(sA) + j * 4096, 128, 256);
         mma_tf32_ss<CG>(tbase, adesc, bdesc, idesc, j > 0);
       }
       if (cgroup > 0 && (((r * KS + j + 1) & (cgroup - 1)) == 0)) mma_commit<CG>(&bar2[(r + j) & 7]);   // commit every `cgroup` (power of 2) MMAs, nobody waits
     }
+    const long long t1 = clock64();
     mma_commit<CG>(&bar);
+    const long long t2 = clock64();
     mbar_wait(&bar, 0);
-    if (cyc) cyc[0] = clock64() - t0;
+    if (cyc) { cyc[0] = clock64() - t0; cyc[1] = t1 - t0; cyc[2] = t2 - t1; }
   }
+#endif
   mbar_wait(&bar, 0);
   tc_fence_after();
   for (int c0 = 0; c0 < N; c0 += 8) {
@@ -92,12 +135,20 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
 
 int main(int argc, char** argv) {
   int cg = argc > 1 ? atoi(argv[1]) : 1, ts = argc > 2 ? atoi(argv[2]) : 0, N = argc > 3 ? atoi(argv[3]) : 176, KS = argc > 4 ? atoi(argv[4]) : 7;
-  int rep = argc > 5 ? atoi(argv[5]) : 1, probe = argc > 6 ? atoi(argv[6]) : 0, cgroup = argc > 7 ? atoi(argv[7]) : 0;
+  int rep = argc > 5 ? atoi(argv[5]) : 1, probe = argc > 6 ? atoi(argv[6]) : 0, cgroup = argc > 7 ? atoi(argv[7]) : 0, ovl = argc > 8 ? atoi(argv[8]) : 0;
   const int M = 128 * cg, K = KS * 8;
-  std::vector<float> A((size_t)M * K), B((size_t)N * K), Bp((size_t)N * K), D((size_t)M * N, -1.f), R((size_t)M * N);
+  std::vector<float> A((size_t)M * K + (size_t)2 * 128 * K + 2 * KS * 1024), B((size_t)N * K), Bp((size_t)N * K), D((size_t)M * N, -1.f), R((size_t)M * N);
   uint32_t s = 12345;
   auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (int)((s >> 20) % 9) - 4; };
   for (auto& v : A) v = rnd() / 4.0f;
+  if (ovl) {
+    float* S = A.data() + (size_t)2 * 128 * K;
+    for (int m = 0; m < M; ++m)
+      for (int k = 0; k < K; ++k) {
+        int rk = m / 128, ml = m % 128, j = k / 8, kk = k % 8;
+        A[(size_t)m * K + k] = S[(size_t)rk * KS * 1024 + j * 1024 + (ml / 8) * 36 + 4 * (ml % 8) + kk];
+      }
+  }
   if (probe) for (auto& v : A) v = 1.0f + 0.75f / 2048.0f;      // 1 + 0.75 ulp_tf32/2...: RNE -> 1 + 2^-10, truncation -> 1
   if (probe) for (auto& v : B) v = 0.0f;
   if (probe) for (int n = 0; n < N; ++n) B[(size_t)n * K] = 1.0f;   // picks A[m][0]
@@ -125,14 +176,16 @@ int main(int argc, char** argv) {
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  long long* dcyc; CK(cudaMalloc(&dcyc, 8)); CK(cudaMemset(dcyc, 0, 8));
-  void (*fn)(const float*, const float*, float*, int, int, int, long long*, int) =
+  long long* dcyc; CK(cudaMalloc(&dcyc, 32)); CK(cudaMemset(dcyc, 0, 32));
+  void (*fn)(const float*, const float*, float*, int, int, int, long long*, int, int) =
       cg == 1 ? (ts ? k_gemm<1, true> : k_gemm<1, false>) : (ts ? k_gemm<2, true> : k_gemm<2, false>);
   CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K, rep, dcyc, cgroup));
+  CK(cudaLaunchKernelEx(&cfg, fn, (const float*)dA, (const float*)dB, dD, N, K, rep, dcyc, cgroup, ovl));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
-  long long hc = 0; CK(cudaMemcpy(&hc, dcyc, 8, cudaMemcpyDeviceToHost));
+  long long hcs[4]; CK(cudaMemcpy(hcs, dcyc, 32, cudaMemcpyDeviceToHost));
+  long long hc = hcs[0];
+  printf("issue timing cg=%d ts=%d N=%d: %d MMAs issued in %lld cycles (%.1f each), commit %lld, all complete after %lld\n", cg, ts, N, rep * KS, hcs[1], (double)hcs[1] / (rep * KS), hcs[2], hcs[0]);
   if (rep > 1) printf("timing cg=%d ts=%d N=%d KS=%d rep=%d commit-every=%d : %.1f cycles per MMA\n", cg, ts, N, KS, rep, cgroup, (double)hc / ((double)rep * KS));
   if (probe) { printf("rounding probe: A = 1 + 0.75*2^-11 (tf32 ulp 2^-10): D[0][0] = %.10f  (1.0 = truncation, 1.0009765625 = round-to-nearest)\n", D[0]); return 0; }
   double maxerr = 0; long bad = 0;

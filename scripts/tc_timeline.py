@@ -48,7 +48,7 @@ show("synthesis", [("producer", list(range(0, 8)), ["wait aempty", "wait xfull",
                    ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
 print("   launch ms", e0.elapsed_time(e1))
 e0.record(); plan.analysis_step(4, r, z, c); e1.record()
-show("analysis", [("producer", list(range(0, 4)), ["wait aempty", "wait r tile", "wait::st", "tmem_st issue", "fence+arrive", "round pass"]),
-                  ("epilogue", list(range(4, 12)), ["wait dfull", "-", "-"]),
-                  ("mma", [12], ["wait dempty", "wait afull", "wait weights"])])
+show("analysis", [("epilogue", list(range(0, 8)), ["wait dfull", "-", "-"]),
+                  ("mma", [8], ["wait dempty", "wait r tiles", "wait weights"]),
+                  ("loader", [9], ["wait rempty", "wait rfull", "-"])])
 print("   launch ms", e0.elapsed_time(e1))
