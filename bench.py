@@ -356,6 +356,16 @@ def main():
                 "avg_launch_ms": avg_ms, "launches_per_step": len(tk[dom]),
                 "share_of_step": tot[dom] / sum(tot.values()),
                 "per_kernel_ms_per_step": tot, "algorithmic_flops_per_launch": alg["conv_flops"]}
+        # both kernels against both ceilings: the analysis step (reads AND rewrites the code: AI 82 FLOP/B) is HBM-bound,
+        # the synthesis step (reads it once: AI 165 FLOP/B) is tensor-bound
+        roof["kernels"] = {}
+        for kname in tot:
+            ms = tot[kname] / len(tk[kname])
+            zb = (2 if kname == "analysis" else 1) * alg["z_pass"]
+            roof["kernels"][kname] = {"bound": "hbm" if kname == "analysis" else "tensor", "avg_launch_ms": ms,
+                                      "tflops": alg["conv_flops"] / (ms * 1e-3) / 1e12, "frac_tensor": alg["conv_flops"] / (ms * 1e-3) / 1e12 / tf32_peak,
+                                      "gbs": zb / (ms * 1e-3) / 1e9, "frac_hbm": zb / (ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                                      "algorithmic_bytes_per_launch": zb}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -429,9 +429,9 @@ extern "C" int cdl_code_export(cdl_plan_t* p, const float* code, float* z, void*
     if (code != z) CDL_CUDA(cudaMemcpyAsync(z, code, p->code_bytes, cudaMemcpyDeviceToDevice, st));
     return CDL_OK;
   }
-  const long long Q = p->g.coarse_vol();
-  dim3 grid((unsigned)((Q + 31) / 32), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
-  tc::k_code_export<<<grid, 256, 0, st>>>(code, z, Q, p->g.Qw, p->g.M);
+  const int R = p->g.Qd * p->g.Qh;
+  dim3 grid((unsigned)(R * ceil_div(p->g.Qw, 32)), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
+  tc::k_code_export<<<grid, 256, 0, st>>>(code, z, R, p->g.Qw, p->g.M);
   CDL_LAUNCH_CHECK(p);
   return CDL_OK;
 }
@@ -443,9 +443,9 @@ extern "C" int cdl_code_import(cdl_plan_t* p, const float* z, float* code, void*
     if (code != z) CDL_CUDA(cudaMemcpyAsync(code, z, p->code_bytes, cudaMemcpyDeviceToDevice, st));
     return CDL_OK;
   }
-  const long long Q = p->g.coarse_vol();
-  dim3 grid((unsigned)((Q + 31) / 32), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
-  tc::k_code_import<<<grid, 256, 0, st>>>(z, code, Q, p->g.Qw, p->g.M);
+  const int R = p->g.Qd * p->g.Qh;
+  dim3 grid((unsigned)(R * ceil_div(p->g.Qw, 32)), (unsigned)ceil_div(tc::kKB, 32), (unsigned)p->g.N);
+  tc::k_code_import<<<grid, 256, 0, st>>>(z, code, R, p->g.Qw, p->g.M);
   CDL_LAUNCH_CHECK(p);
   return CDL_OK;
 }

@@ -237,7 +237,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
     };
     float zr[8 * kMaxB];
     float* zs; int n, valid;
-    prefetch_rows(pair + npairs);
+#ifndef CDL_ANA_PF
+#define CDL_ANA_PF 2          // bulk L2 prefetch distance in tiles (3+ thrashes L2: measured 4.3 -> 5.1 ms)
+#endif
+#ifndef CDL_ANA_EVICT
+#define CDL_ANA_EVICT 2       // L2 evict-first on the code stores (1) and loads (2): the lines are dead after use
+#endif
+#pragma unroll
+    for (int a = 1; a < CDL_ANA_PF; ++a) prefetch_rows(pair + a * npairs);
+#if CDL_ANA_EVICT >= 1
+    const uint64_t pol = l2_policy_evict_first();
+#endif
     if (pair < p.ntiles) {
       site(pair, zs, n, valid);
 #pragma unroll
@@ -253,7 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
         named_bar_sync(3, 32 * kAEpiWarps);
         n_tau = n;
       }
-      prefetch_rows(tile + 2 * npairs);
+      prefetch_rows(tile + CDL_ANA_PF * npairs);
       float* zs2 = zs; int n2 = n, valid2 = 0;
       if (tile + npairs < p.ntiles) site(tile + npairs, zs2, n2, valid2);
       const int ld2 = valid2 && !p.first;
@@ -275,8 +285,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           zr[8 * b + i] = soft_threshold(__fsub_rn(zr[8 * b + i], __uint_as_float(u[i] ^ usign)), tt[i]);
+#if CDL_ANA_EVICT >= 1
+        stg256_pred_hint(zs + kCodeBlk * b, *reinterpret_cast<const float(*)[8]>(&zr[8 * b]), valid, pol);
+#else
         stg256_pred(zs + kCodeBlk * b, *reinterpret_cast<const float(*)[8]>(&zr[8 * b]), valid);
+#endif
+#if CDL_ANA_EVICT >= 2
+        ldg256_pred_hint(zs2 + kCodeBlk * b, *reinterpret_cast<float(*)[8]>(&zr[8 * b]), ld2, pol);
+#else
         ldg256_pred(zs2 + kCodeBlk * b, *reinterpret_cast<float(*)[8]>(&zr[8 * b]), ld2);   // same registers: tile i+1, block b
+#endif
         }
       }
       tc_fence_before();                           // accumulator fully read: hand the TMEM slot back to the MMA warp

@@ -249,6 +249,22 @@ __device__ __forceinline__ void stg256_pred(float* p, const float (&v)[8], int o
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t@p st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};\n\t}"
                ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p), "r"(ok) : "memory");
 }
+// streaming variants: the line is dead once written (evict-first in L2)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void stg256_pred_hint(float* p, const float (&v)[8], int ok, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t@p st.global.L2::cache_hint.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7}, %10;\n\t}"
+               ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p), "r"(ok), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ldg256_pred_hint(const float* p, float (&v)[8], int ok, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %9, 0;\n\t"
+               "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0; mov.b32 %4, 0; mov.b32 %5, 0; mov.b32 %6, 0; mov.b32 %7, 0;\n\t"
+               "@p ld.global.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %10;\n\t}"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p), "r"(ok), "l"(pol));
+}
 // volatile shared-memory 8-byte load: keeps its place in program order, so a run of them is issued back to back
 __device__ __forceinline__ void lds64(const float* p, float& a, float& b) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(smem_u32(p)));

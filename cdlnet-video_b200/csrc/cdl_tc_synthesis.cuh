@@ -415,40 +415,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
 }
 
 // ---- code layout conversion: internal quad-blocked channels-last <-> reference (N,M,Qd,Qh,Qw) ----
-// 32 x 32 tile transpose through shared memory; Q = Qd*Qh*Qw sites per sample, R = Qd*Qh rows per sample
-__device__ __forceinline__ size_t code_elem(long long n, long long R, int Qw, long long q, int m) {
-  const long long row = n * R + q / Qw;
-  return code_site_offset((size_t)row, Qw, (int)(q % Qw)) + (size_t)(m >> 3) * kCodeBlk + (m & 7);
+// One block = 32 consecutive sites of one row x 32 subbands, transposed through shared memory.  On the internal side
+// that tile is 8 contiguous 512-byte pieces (4 w-blocks x 2 parities, 4 subband blocks each): one float4 per lane.
+// grid = (rows * ceil(Qw/32), 176/32 rounded up, N); R = Qd*Qh rows per sample.
+__device__ __forceinline__ void code_tile_piece(int warp, int lane, int& qloc, int& mloc) {
+  const int wb = warp >> 1, par = warp & 1;                 // piece = (w-block, parity); lane = float4 index inside it
+  qloc = 8 * wb + 2 * ((lane & 7) >> 1) + par;              // site inside the 32-site segment
+  mloc = 8 * (lane >> 3) + 4 * (lane & 1);                  // first of 4 subbands inside the 32-subband slab
 }
-__global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ zcl, float* __restrict__ z, long long Q, int Qw, int M) {
-  __shared__ float t[32][33];
-  const long long q0 = (long long)blockIdx.x * 32;
+__global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ zcl, float* __restrict__ z, int R, int Qw, int M) {
+  __shared__ float t[32][33];                               // [site][subband]
+  const int nseg = (Qw + 31) >> 5;
+  const int row = blockIdx.x / nseg, qw0 = (blockIdx.x % nseg) * 32;
   const int m0 = blockIdx.y * 32, n = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const long long q = q0 + r; const int m = m0 + tx;
-    t[r][tx] = (q < Q && m < kKB) ? zcl[code_elem(n, Q / Qw, Qw, q, m)] : 0.0f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int qloc, mloc;
+  code_tile_piece(warp, lane, qloc, mloc);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (qw0 + qloc < Qw && m0 + mloc < kKB)
+    v = *reinterpret_cast<const float4*>(zcl + code_site_offset((size_t)n * R + row, Qw, qw0 + qloc) + (size_t)((m0 + mloc) >> 3) * kCodeBlk + ((m0 + mloc) & 7));
+  t[qloc][mloc] = v.x; t[qloc][mloc + 1] = v.y; t[qloc][mloc + 2] = v.z; t[qloc][mloc + 3] = v.w;
+  __syncthreads();
+  const size_t Q = (size_t)R * Qw;
+  for (int r = warp; r < 32; r += 8) {
+    const int m = m0 + r, qw = qw0 + lane;
+    if (m < M && qw < Qw) z[((size_t)n * M + m) * Q + (size_t)row * Qw + qw] = t[lane][r];
+  }
+}
+__global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z, float* __restrict__ zcl, int R, int Qw, int M) {
+  __shared__ float t[32][33];
+  const int nseg = (Qw + 31) >> 5;
+  const int row = blockIdx.x / nseg, qw0 = (blockIdx.x % nseg) * 32;
+  const int m0 = blockIdx.y * 32, n = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t Q = (size_t)R * Qw;
+  for (int r = warp; r < 32; r += 8) {
+    const int m = m0 + r, qw = qw0 + lane;
+    t[lane][r] = (m < M && qw < Qw) ? z[((size_t)n * M + m) * Q + (size_t)row * Qw + qw] : 0.0f;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int m = m0 + r; const long long q = q0 + tx;
-    if (m < M && q < Q) z[((long long)n * M + m) * Q + q] = t[tx][r];
-  }
-}
-__global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z, float* __restrict__ zcl, long long Q, int Qw, int M) {
-  __shared__ float t[32][33];
-  const long long q0 = (long long)blockIdx.x * 32;
-  const int m0 = blockIdx.y * 32, n = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int m = m0 + r; const long long q = q0 + tx;
-    t[r][tx] = (m < M && q < Q) ? z[((long long)n * M + m) * Q + q] : 0.0f;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const long long q = q0 + r; const int m = m0 + tx;
-    if (q < Q && m < kKB) zcl[code_elem(n, Q / Qw, Qw, q, m)] = t[tx][r];
-  }
+  int qloc, mloc;
+  code_tile_piece(warp, lane, qloc, mloc);
+  if (qw0 + qloc < Qw && m0 + mloc < kKB)
+    *reinterpret_cast<float4*>(zcl + code_site_offset((size_t)n * R + row, Qw, qw0 + qloc) + (size_t)((m0 + mloc) >> 3) * kCodeBlk + ((m0 + mloc) & 7)) =
+        make_float4(t[qloc][mloc], t[qloc][mloc + 1], t[qloc][mloc + 2], t[qloc][mloc + 3]);
 }
 
 }  // namespace tc

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-end style check on the B200 box: GPU parity tests, smoke, bench (both arms), ncu launch list + full capture.
+# Round-end style check on the B200 box: GPU parity tests, smoke, bench (both arms), ncu launch list.
+# (the ncu --set full capture of the two tensor-core kernels is a separate call: scripts/gpu_ncu.sh)
 # Usage: scripts/gpu_check.sh [tag]
 TAG=${1:-r01}
 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
@@ -14,6 +15,4 @@ CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-breakdown"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on -k "regex:^k_tc_(analysis|synthesis)" -s 10 -c 4 -f -o gpurun_out/${TAG}_prof $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
-echo "ncu full exit $?"
 ls -la gpurun_out | tail -12
