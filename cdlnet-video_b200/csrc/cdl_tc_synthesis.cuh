@@ -127,24 +127,19 @@ __device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs,
     cur[i].x += x0[i]; cur[i].y += x1[i];
     *reinterpret_cast<float2*>(rowp[i] + 4 + 2 * lane) = cur[i];
   }
-  if (lane == 0) {                                  // left spill: fine w = 2*qw0 - 3 .. -1  (tile columns 1..3)
+  // Spill voxels outside the warp's 64 own columns: lane 0 holds the left three (fine w = 2*qw0 - 3 .. -1 = tile
+  // columns 1..3), lane 31 the right two (2*qw0 + 64, 65 = tile columns 68, 69).  One float4 read-modify-write at a
+  // lane-dependent address serves both in a single divergent region (two lanes active) instead of two.
+  if (lane == 0 || lane == 31) {
+    const int off = lane ? 68 : 0;
     float4 q[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] = *reinterpret_cast<const float4*>(rowp[i]);
+    for (int i = 0; i < NR; ++i) q[i] = *reinterpret_cast<const float4*>(rowp[i] + off);
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      q[i].y += e1[i]; q[i].z += e2[i]; q[i].w += e3[i];
-      *reinterpret_cast<float4*>(rowp[i]) = q[i];
-    }
-  }
-  if (lane == 31) {                                 // right spill: fine w = 2*qw0 + 64, 65  (tile columns 68, 69)
-    float2 q[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] = *reinterpret_cast<const float2*>(rowp[i] + 68);
-#pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      q[i].x += f5[i]; q[i].y += f6[i];
-      *reinterpret_cast<float2*>(rowp[i] + 68) = q[i];
+      q[i].x += lane ? f5[i] : 0.0f; q[i].y += lane ? f6[i] : e1[i];
+      q[i].z += lane ? 0.0f : e2[i]; q[i].w += lane ? 0.0f : e3[i];
+      *reinterpret_cast<float4*>(rowp[i] + off) = q[i];
     }
   }
 }
