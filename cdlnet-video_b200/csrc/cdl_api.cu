@@ -92,6 +92,9 @@ struct cdl_plan {
   size_t wAtc_layer, wBtc_layer;
   int sm_count;
   bool have_weights;
+  // cdl_forward only: the analysis step's rounding pass re-arms the residual buffer with -yp for the next synthesis
+  const float* fused_yp = nullptr;
+  bool rbuf_armed = false;
   size_t code_bytes;   // bytes of the sparse code in the plan's internal layout
   Offsets off;
   uint64_t launches;
@@ -591,7 +594,10 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     {
       const long long n4 = (long long)p->g.N * p->g.fine_vol() / 4;
       long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4);
+      float* rbuf = reinterpret_cast<float*>((char*)ws + p->off.rbuf);
+      const bool arm = p->fused_yp && r == rbuf;          // the plan's own residual buffer, dead once read here
+      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4, arm ? p->fused_yp : nullptr, arm ? rbuf : nullptr);
+      p->rbuf_armed = arm;
       CDL_LAUNCH_CHECK(p);
     }
     CUtensorMap rmap0, rmap1;
@@ -628,7 +634,9 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
   if (p->tc_syn) {
     cudaStream_t st = (cudaStream_t)stream_;
     const long long nfine = (long long)p->g.N * p->g.fine_vol();
-    if (residual) {
+    if (residual && p->rbuf_armed && ws && out == reinterpret_cast<float*>((char*)ws + p->off.rbuf) && yp == p->fused_yp) {
+      p->rbuf_armed = false;                               // out already holds -yp (written by the previous rounding pass)
+    } else if (residual) {
       long long n4 = nfine / 4, blocks = (n4 + 255) / 256;
       if (blocks > 148 * 8) blocks = 148 * 8;
       tc::k_neg_copy<<<(int)blocks, 256, 0, st>>>(yp, out, n4);        // out <- -yp ; the scatter-add completes B z - yp
@@ -694,10 +702,13 @@ extern "C" int cdl_forward(cdl_plan_t* p, const float* yp, const float* mask_p, 
   // the tensor-core kernels keep the code channels-last in the workspace; the fp32 kernels work in place on z
   float* code = p->tc_ana ? reinterpret_cast<float*>((char*)ws + p->off.code) : z;
   int rc = cdl_analysis_step(p, 0, 1, yp, c, code, ws, stream_);                   // model/net.py:85,200
+  p->rbuf_armed = false;
   for (int k = 1; k < p->g.K && !rc; ++k) {                                        // model/net.py:86-87,204-205
     rc = cdl_synthesis_step(p, k, 1, code, yp, mask_p, rbuf, ws, stream_);
+    p->fused_yp = (p->tc_syn && k + 1 < p->g.K) ? yp : nullptr;                     // another residual synthesis follows
     if (!rc) rc = cdl_analysis_step(p, k, 0, rbuf, c, code, ws, stream_);
   }
+  p->fused_yp = nullptr; p->rbuf_armed = false;
   if (!rc) rc = cdl_synthesis_step(p, 0, 0, code, nullptr, nullptr, xphat, ws, stream_);   // D = B[0], model/net.py:90,210
   if (!rc) rc = cdl_code_export(p, code, z, stream_);
   return rc;
