@@ -80,3 +80,43 @@ def test_tf32_cfg2_full_size_parity():
     assert ex <= TOL, ex
     assert abs(p1 - p0) <= 0.01
     assert 0.01 < nnz < 0.5
+
+
+@pytest.mark.parametrize("dims,N,M", [((6, 20, 40), 2, 169), ((7, 13, 44), 1, 100), ((8, 32, 64), 1, 169)])
+def test_code_layout_roundtrip(dims, N, M):
+    """The plan-internal quad-blocked code layout <-> the reference's (N,M,Qd,Qh,Qw): import then export is the
+    identity, bit for bit, also when Qw is not a multiple of the 8-site block (ragged rows are padded internally)."""
+    d = torch.device("cuda", 0)
+    plan = cb.Plan(3, N, 1, M, 2, dims, (7, 7, 7), 2, precision="tf32")
+    if plan.precision != "tf32":
+        pytest.skip("geometry not on the tensor-core path")
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(N, M, *plan.coarse, generator=g).to(d)
+    code = plan.import_code(z)
+    back = plan.export_code(code)
+    assert back.shape == z.shape and torch.equal(back, z)
+
+
+def test_stepwise_equals_fused_tf32():
+    """cdl_forward (which fuses the -yp re-arm of the residual buffer into the rounding pass) == the step API driven
+    from the host, on the tensor-core path.  The scatter-add order differs run to run: compare at 1e-5."""
+    d = torch.device("cuda", 0)
+    dims, N, M, K = (8, 32, 64), 2, 169, 4
+    A, B, g = _weights(M, K, 3, 0.7 / np.sqrt(2.0 * M * 343 / 8))
+    t = (torch.rand(K, 2, M, generator=g) * 0.01).to(d)
+    y = torch.rand(N, 1, *dims, generator=g).to(d)
+    c = torch.tensor([0.1, 0.06], device=d)
+    plan = cb.Plan(3, N, 1, M, K, dims, (7, 7, 7), 2, precision="tf32")
+    plan.set_weights([a.to(d) for a in A], [b.to(d) for b in B], t)
+    xhat, z = plan.denoise(y, None, c)
+    yp, _, mean = plan.preprocess(y)
+    code, r = plan.new_code(), torch.empty_like(yp)
+    plan.analysis_step(0, yp, code, c, first=True)
+    for k in range(1, K):
+        plan.synthesis_step(k, code, r, yp, None, residual=True)
+        plan.analysis_step(k, r, code, c)
+    xp = torch.empty_like(yp)
+    plan.synthesis_step(0, code, xp, residual=False)
+    x2 = plan.postprocess(xp, mean)
+    assert (x2 - xhat).abs().max().item() <= 1e-5
+    assert (plan.export_code(code) - z).abs().max().item() <= 1e-5
