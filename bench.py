@@ -365,7 +365,12 @@ def main():
             roof["kernels"][kname] = {"bound": "hbm" if kname == "analysis" else "tensor", "avg_launch_ms": ms,
                                       "tflops": alg["conv_flops"] / (ms * 1e-3) / 1e12, "frac_tensor": alg["conv_flops"] / (ms * 1e-3) / 1e12 / tf32_peak,
                                       "gbs": zb / (ms * 1e-3) / 1e9, "frac_hbm": zb / (ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
-                                      "algorithmic_bytes_per_launch": zb}
+                                      "algorithmic_bytes_per_launch": zb,
+                                      "floor_ms": max(zb / (peaks.get("hbm_gbs", 6650.0) * 1e9), alg["conv_flops"] / (tf32_peak * 1e12)) * 1e3}
+        # north_star's "fraction of the per-iteration roofline": each kernel at the higher of its HBM and tensor floors
+        it_floor = sum(v["floor_ms"] for v in roof["kernels"].values())
+        it_ms = sum(v["avg_launch_ms"] for v in roof["kernels"].values())
+        roof["per_iteration"] = {"floor_ms": it_floor, "achieved_ms": it_ms, "frac": it_floor / it_ms}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -101,10 +101,20 @@ def main():
         ms = time_steps(fn, args.steps, args.warmup, world)
         vox = D * H * W
         flops = 2 * K * 2.0 * (vox / 8) * M * 343
+        # per-iteration roofline (north_star): analysis = 2 passes of the 176-subband code over HBM, synthesis = tensor pipe
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
+        zbytes = (vox / 8) * 176 * 4.0
+        kflops = 2.0 * (vox / 8) * M * 343
+        tf32 = peaks.get("bf16_tflops_sustained", 1400.0) / 2 * 1e12
+        floor_s = K * (max(2 * zbytes / (peaks["hbm_gbs"] * 1e9), kflops / tf32) + max(zbytes / (peaks["hbm_gbs"] * 1e9), kflops / tf32)) / world
         out.update(workload=f"cfg5: CDLNetVideo K=30 M=169 7x7x7 s=2, one {D}x{H}x{W} clip, temporal slabs over {world} GPU(s), "
                             f"halo {g['overlap']} frames per seam per iteration", precision=den.plan.precision, scaling="strong",
                    value=vox / (ms * 1e-3) / 1e6, ms_per_step=ms, tflops=flops / (ms * 1e-3) / 1e12,
-                   frac_of_tf32_roofline=flops / (ms * 1e-3) / 1e12 / 688.1 / world)
+                   frac_of_tf32_roofline=flops / (ms * 1e-3) / 1e12 / 688.1 / world,
+                   frac_of_per_iteration_roofline=floor_s / (ms * 1e-3))
     else:
         if args.config in ("cfg1", "cfg1b"):
             kind, (K, M, P, s, C), shape, use_mask = "cdl", ((30, 169, 7, 2, 1) if args.config == "cfg1" else (20, 32, 7, 1, 1)), (1, 1, 256, 256), False

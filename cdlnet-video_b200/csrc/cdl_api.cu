@@ -652,6 +652,7 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
     a.dbg = g_tc_dbg;
+    a.dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
     a.a_lo = 0;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;

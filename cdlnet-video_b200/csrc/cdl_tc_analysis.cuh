@@ -26,7 +26,6 @@
 #pragma once
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
-#include <cstdio>
 
 namespace cdl {
 namespace tc {
@@ -77,7 +76,7 @@ struct AnaTcParams {
   int tiles_w, tiles_h; // pair tiles along w and h (16 x 16 sites)
   int ntiles;           // N * Qd * tiles_h * tiles_w
   long long* dbg;       // optional [grid][24 warps][8] cycle counters
-  int dbg_mode;         // development aid: 2 = epilogue skips the code traffic (results invalid)
+  int dbg_mode;         // development aid (results invalid): 2 = epilogue skips the code traffic, 16 = no TMA loads, 32 = no MMAs
 };
 
 constexpr size_t kAnaSmemB = (size_t)kKSteps * kNAH * 8 * sizeof(float);      // 137984
@@ -312,8 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
     // ============================== MMA issue (leader CTA) ==============================
     // The whole warp runs this loop converged and one elected lane issues (mma_tf32_ss_warp): the issue cost per MMA
     // stays far below the tensor pipe's 88 cycles, so the warp runs ahead of the pipe (its queue holds ~18 MMAs) and
-    // the commits / barrier waits cost nothing.  TMEM base is 0 by construction (the CTA owns all 512 columns).
-    if (tbase != 0 && lane == 0) printf("k_tc_analysis: unexpected TMEM base %u\n", tbase);
+    // the commits / barrier waits cost nothing.
     if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
     if (rank == 0) {
       CDL_TW(tw2, mbar_wait(wbar, 0); mbar_wait_cluster(wready, 0));

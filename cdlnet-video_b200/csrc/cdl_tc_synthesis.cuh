@@ -51,6 +51,7 @@ struct SynTcParams {
   int seg, nseg, nunits; // a CTA pair sweeps `seg` consecutive coarse frames of one (n, h-tile, w-tile) column per unit
   int a_lo;             // 0: A = rna_tf32(z) ; 1: A = rna_tf32(z - rna_tf32(z))  (low part, used by the 3-term final synthesis)
   long long* dbg;
+  int dbg_mode;         // development aid (results invalid): 512 = producers skip the code loads, 1024 = no L2 prefetch
 };
 
 constexpr size_t kSynSmemB = (size_t)2 * kKBSteps * (kNBP / 2) * 8 * sizeof(float);             // 123904
@@ -287,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       const SynTile t = syn_tile(p, pair, npairs, it);
       const SynTile t2 = syn_tile(p, pair, npairs, it + 1 < my_tiles ? it + 1 : it);
       const int qh = t.qh0 + rank * kTH + quad, qw = t.qw0 + lane;
-      const int valid = qh < g.Qh && qw < g.Qw;
+      const int valid = qh < g.Qh && qw < g.Qw && !(p.dbg_mode & 512);
       const float* zs = p.z + code_site_offset(((size_t)t.n * g.Qd + t.qd) * g.Qh + qh, g.Qw, qw);
       // bulk L2 prefetch two tiles ahead (the register refill below already requests tile it+1 during tile it): one
       // contiguous 22.5 KB burst per tile row keeps the DRAM reads sequential
@@ -321,7 +322,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
       int valid2 = 0;
       if (it + 1 < my_tiles) {
         const int qh2 = t2.qh0 + rank * kTH + quad, qw2 = t2.qw0 + lane;
-        valid2 = qh2 < g.Qh && qw2 < g.Qw;
+        valid2 = qh2 < g.Qh && qw2 < g.Qw && !(p.dbg_mode & 512);
         zs2 = p.z + code_site_offset(((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2, g.Qw, qw2);
       }
 #pragma unroll
