@@ -30,7 +30,8 @@ def _run(plan, A, B, t, y, c):
 
 
 @pytest.mark.parametrize("dims,N,M,K", [((8, 32, 64), 1, 169, 3), ((6, 20, 40), 2, 169, 2), ((4, 16, 36), 1, 64, 4),
-                                         ((16, 64, 64), 1, 169, 6), ((7, 13, 44), 1, 100, 3)])
+                                         ((16, 64, 64), 1, 169, 6), ((7, 13, 44), 1, 100, 3), ((8, 32, 64), 2, 169, 1),
+                                         ((6, 36, 72), 1, 169, 2)])
 def test_tf32_small_vs_oracle(dims, N, M, K):
     A, B, g = _weights(M, K, 11, 0.7 / np.sqrt(2.0 * M * 343 / 8))
     t = torch.rand(K, 2, M, 1, 1, 1, generator=g) * 0.01
