@@ -22,7 +22,7 @@ SYMBOLS = [
     "cdl_plan_workspace_bytes", "cdl_plan_precision", "cdl_set_weights", "cdl_reduce_sums",
     "cdl_mean_from_sums", "cdl_center_pad", "cdl_preprocess", "cdl_analysis_step", "cdl_synthesis_step",
     "cdl_forward", "cdl_postprocess", "cdl_denoise", "cdl_plan_host_workspace_bytes", "cdl_denoise_host",
-    "cdl_plan_launch_count", "cdl_plan_code_bytes", "cdl_code_export", "cdl_code_import",
+    "cdl_plan_launch_count", "cdl_plan_code_bytes", "cdl_code_export", "cdl_code_import", "cdl_plan_set_rearm",
 ]
 
 
@@ -102,6 +102,8 @@ def load():
             getattr(lib, name).argtypes = [vp, P(ctypes.c_size_t)]
         lib.cdl_plan_precision.restype = i32
         lib.cdl_plan_precision.argtypes = [vp]
+        lib.cdl_plan_set_rearm.restype = i32
+        lib.cdl_plan_set_rearm.argtypes = [vp, i32]
         lib.cdl_plan_launch_count.restype = i32
         lib.cdl_plan_launch_count.argtypes = [vp, P(ctypes.c_uint64)]
         lib.cdl_set_weights.restype = i32

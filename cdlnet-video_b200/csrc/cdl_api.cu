@@ -93,8 +93,14 @@ struct cdl_plan {
   int sm_count;
   bool have_weights;
   // cdl_forward only: the analysis step's rounding pass re-arms the residual buffer with -yp for the next synthesis
-  const float* fused_yp = nullptr;
-  bool rbuf_armed = false;
+  // Residual re-arm: the analysis step's rounding pass may overwrite its (consumed) input r with -yp so that the next
+  // residual synthesis into the same buffer skips its initialisation pass.  Always on inside cdl_forward (plan-owned
+  // buffer); opt-in for stepwise drivers (cdl_plan_set_rearm), because it clobbers an input.
+  bool rearm_opt = false, rearm_fwd = false;
+  const float* last_yp = nullptr;    // arguments of the last residual synthesis step
+  const float* last_out = nullptr;
+  const float* armed_buf = nullptr;  // buffer currently holding -armed_yp
+  const float* armed_yp = nullptr;
   size_t code_bytes;   // bytes of the sparse code in the plan's internal layout
   Offsets off;
   uint64_t launches;
@@ -452,6 +458,12 @@ extern "C" int cdl_code_import(cdl_plan_t* p, const float* z, float* code, void*
   CDL_LAUNCH_CHECK(p);
   return CDL_OK;
 }
+extern "C" int cdl_plan_set_rearm(cdl_plan_t* p, int enable) {
+  if (!p) return CDL_ERR_NULL;
+  p->rearm_opt = enable != 0;
+  p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
+  return CDL_OK;
+}
 extern "C" int cdl_plan_launch_count(const cdl_plan_t* p, uint64_t* out) {
   if (!p || !out) return CDL_ERR_NULL;
   *out = p->launches;
@@ -594,10 +606,11 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     {
       const long long n4 = (long long)p->g.N * p->g.fine_vol() / 4;
       long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-      float* rbuf = reinterpret_cast<float*>((char*)ws + p->off.rbuf);
-      const bool arm = p->fused_yp && r == rbuf;          // the plan's own residual buffer, dead once read here
-      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4, arm ? p->fused_yp : nullptr, arm ? rbuf : nullptr);
-      p->rbuf_armed = arm;
+      const bool arm = (p->rearm_opt || p->rearm_fwd) && p->tc_syn && !first && p->last_yp && r == p->last_out;   // r is dead once read here
+      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4, arm ? p->last_yp : nullptr,
+                                                                       arm ? const_cast<float*>(r) : nullptr);
+      p->armed_buf = arm ? r : nullptr;
+      p->armed_yp = arm ? p->last_yp : nullptr;
       CDL_LAUNCH_CHECK(p);
     }
     CUtensorMap rmap0, rmap1;
@@ -634,8 +647,10 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
   if (p->tc_syn) {
     cudaStream_t st = (cudaStream_t)stream_;
     const long long nfine = (long long)p->g.N * p->g.fine_vol();
-    if (residual && p->rbuf_armed && ws && out == reinterpret_cast<float*>((char*)ws + p->off.rbuf) && yp == p->fused_yp) {
-      p->rbuf_armed = false;                               // out already holds -yp (written by the previous rounding pass)
+    const bool prearmed = residual && p->armed_buf == out && p->armed_yp == yp;   // out already holds -yp (previous rounding pass)
+    p->armed_buf = nullptr; p->armed_yp = nullptr;
+    p->last_yp = residual ? yp : nullptr; p->last_out = residual ? out : nullptr;
+    if (prearmed) {
     } else if (residual) {
       long long n4 = nfine / 4, blocks = (n4 + 255) / 256;
       if (blocks > 148 * 8) blocks = 148 * 8;
@@ -703,13 +718,13 @@ extern "C" int cdl_forward(cdl_plan_t* p, const float* yp, const float* mask_p, 
   // the tensor-core kernels keep the code channels-last in the workspace; the fp32 kernels work in place on z
   float* code = p->tc_ana ? reinterpret_cast<float*>((char*)ws + p->off.code) : z;
   int rc = cdl_analysis_step(p, 0, 1, yp, c, code, ws, stream_);                   // model/net.py:85,200
-  p->rbuf_armed = false;
+  p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
   for (int k = 1; k < p->g.K && !rc; ++k) {                                        // model/net.py:86-87,204-205
     rc = cdl_synthesis_step(p, k, 1, code, yp, mask_p, rbuf, ws, stream_);
-    p->fused_yp = (p->tc_syn && k + 1 < p->g.K) ? yp : nullptr;                     // another residual synthesis follows
+    p->rearm_fwd = k + 1 < p->g.K;                                                 // another residual synthesis follows
     if (!rc) rc = cdl_analysis_step(p, k, 0, rbuf, c, code, ws, stream_);
   }
-  p->fused_yp = nullptr; p->rbuf_armed = false;
+  p->rearm_fwd = false; p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
   if (!rc) rc = cdl_synthesis_step(p, 0, 0, code, nullptr, nullptr, xphat, ws, stream_);   // D = B[0], model/net.py:90,210
   if (!rc) rc = cdl_code_export(p, code, z, stream_);
   return rc;

@@ -77,6 +77,11 @@ class Plan:
     def precision(self):
         return {0: "fp32", 1: "tf32"}[self.lib.cdl_plan_precision(self.handle)]
 
+    def set_rearm(self, enable=True):
+        """Stepwise drivers only: let analysis_step overwrite its consumed input r with -yp for the next residual synthesis
+        into the same buffer (see cdl_plan_set_rearm in include/cdl_b200.h)."""
+        _lib.check(self.lib.cdl_plan_set_rearm(self.handle, 1 if enable else 0), "cdl_plan_set_rearm")
+
     def launch_count(self):
         n = ctypes.c_uint64()
         _lib.check(self.lib.cdl_plan_launch_count(self.handle, ctypes.byref(n)))

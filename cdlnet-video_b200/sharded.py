@@ -50,6 +50,9 @@ class PlanOps:
 
     def __init__(self, plan, sum_plan):
         self.plan, self.sum_plan = plan, sum_plan
+        # SlabRank alternates synthesis(out = r) / [halo add] / analysis(r) on one buffer and never reads r after the
+        # analysis: let the analysis step re-arm it with -yp (saves the initialisation pass of every residual synthesis)
+        plan.set_rearm(True)
 
     def owned_sums(self, y_owned):                    # (2N,) float64: sum(y), count
         return self.sum_plan.reduce_sums(y_owned.contiguous())

@@ -111,6 +111,13 @@ int cdl_analysis_step(cdl_plan_t* plan, int k, int first, const float* r, const 
 /* One synthesis step  out <- mask_p * B_k z - yp  (residual != 0) or out <- B_k z (residual == 0). */
 int cdl_synthesis_step(cdl_plan_t* plan, int k, int residual, const float* code, const float* yp, const float* mask_p, float* out, void* workspace, void* stream);
 
+/* Opt-in for stepwise drivers that alternate cdl_synthesis_step(residual, out = R) and cdl_analysis_step(r = R) on the
+ * SAME buffer R with the same yp (the loop of model/net.py:204-205 unrolled by the caller, e.g. the temporal-slab
+ * driver): the analysis step may then overwrite R - its input, dead once read - with -yp, and the next residual
+ * synthesis into R skips its own initialisation pass (one launch and one image pass less per iteration).  Only the
+ * tensor-core path uses it; cdl_forward always does this on its own buffer.  enable = 0 restores const semantics.    */
+int cdl_plan_set_rearm(cdl_plan_t* plan, int enable);
+
 /* All K iterations + D z:  z (N,M,coarse) and xphat (N,C,fine) out.                              */
 int cdl_forward(cdl_plan_t* plan, const float* yp, const float* mask_p, const float* c, float* z, float* xphat, void* workspace, void* stream);
 /* post_process / post_process_3d (model/utils.py:24-33, 89-98): crop the stride padding, add the mean. */
