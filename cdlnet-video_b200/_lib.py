@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libcdl_b200.so")
     tmp = LIB_PATH + ".tmp%d" % os.getpid()
     extra = ["-DCDL_TC_PROFILE"] if os.environ.get("CDL_TC_PROFILE") else []      # per-role cycle counters (dev aid)
-    extra += os.environ.get("CDL_NVCC_DEFS", "").split()                              # e.g. -DCDL_ANA_ROWS=7 (tuning experiments)
+    extra += os.environ.get("CDL_NVCC_DEFS", "").split()                              # e.g. -DCDL_ANA_PF=1 (tuning experiments)
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-o", tmp, *sources()]
     if verbose:
         print(" ".join(cmd), flush=True)

@@ -8,11 +8,8 @@
 // development aid: per-warp cycle counters of the barrier waits (enabled when a debug buffer is set)
 #ifdef CDL_TC_PROFILE
 #define CDL_TW(acc, stmt) do { long long t0__ = clock64(); stmt; acc += clock64() - t0__; } while (0)
-// event trace of block 0 (dbg_mode bit 3): raw clock64 stamps behind the per-warp counters
-#define CDL_EV(cond, idx) do { if ((p.dbg_mode & 8) && p.dbg && blockIdx.x == 0 && (cond)) p.dbg[148 * 24 * 8 + (idx)] = clock64(); } while (0)
 #else
 #define CDL_TW(acc, stmt) do { stmt; } while (0)
-#define CDL_EV(cond, idx) do {} while (0)
 #endif
 
 namespace cdl {
