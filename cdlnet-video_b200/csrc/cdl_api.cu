@@ -15,6 +15,7 @@
 #include "cdl_prepost.cuh"
 #include "cdl_tc_analysis.cuh"
 #include "cdl_tc_synthesis.cuh"
+#include "cdl_tc2_analysis.cuh"
 
 using namespace cdl;
 
@@ -62,6 +63,20 @@ static int make_fine_tmap(CUtensorMap* out, const float* base, const Geo& g, int
   return r == CUDA_SUCCESS ? CDL_OK : CDL_ERR_UNSUPPORTED;
 }
 
+static int make_tmap2d(CUtensorMap* out, const float* base, const Geo& g) {
+  // r viewed as (N, C, H, W): a box is the analysis halo tile of the 2-D tensor-core path, 40 floats x 22 rows x C
+  // channels; out-of-range coordinates read as zero = the convolution's padding
+  const cuuint64_t W = (cuuint64_t)g.Fw, H = (cuuint64_t)g.Fh;
+  const cuuint64_t gdim[4] = {W, H, (cuuint64_t)g.C, (cuuint64_t)g.N};
+  const cuuint64_t gstr[3] = {W * 4, W * H * 4, W * H * g.C * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)tc2::kSW, (cuuint32_t)tc2::kRows, (cuuint32_t)g.C, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CDL_OK : CDL_ERR_UNSUPPORTED;
+}
+
 // development aid (not part of the ABI): cycle counters of the tensor-core kernels' warp roles
 static long long* g_tc_dbg = nullptr;
 extern "C" void cdl__debug_set_buffer(long long* p) { g_tc_dbg = p; }
@@ -90,6 +105,12 @@ struct cdl_plan {
   float* wBtc;         // [K][2 ranks][176*176]
   float* wBtc_lo;      // layer 0 only: tf32(W - tf32(W)), for the 3-term final synthesis
   size_t wAtc_layer, wBtc_layer;
+  // experimental tcgen05 analysis for 2D, 7x7, s = 1, C <= 3, M <= 64 (cdl_tc2_analysis.cuh); opt-in with CDL_TC2D=1
+  bool tc2_ana;
+  int tc2_Ng;          // GEMM N: M rounded up to 16
+  float* wA2;          // [K][7*C][Ng*8] tf32 filters in UMMA layout
+  size_t wA2_layer;
+  size_t tc2_smem;
   int sm_count;
   bool have_weights;
   // cdl_forward only: the analysis step's rounding pass re-arms the residual buffer with -yp for the next synthesis
@@ -275,6 +296,15 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   const bool tc_geom = nd3 && Pd == 7 && Ph == 7 && Pw == 7 && s == 2 && d->C == 1 && d->M <= tc::kNA && (L.fine[2] % 4) == 0 && (L.fine[1] % 2) == 0 && !d->has_mask;
   if (d->precision == CDL_PREC_TF32 && tc_geom) { p->tc_ana = true; p->tc_syn = (getenv("CDL_TC_SYN") ? atoi(getenv("CDL_TC_SYN")) != 0 : true); p->precision_eff = CDL_PREC_TF32; }
 
+  // experimental 2-D tensor-core analysis (the synthesis stays on the fp32 CUDA-core kernel, same planar code layout)
+  const bool tc2_geom = !nd3 && Ph == 7 && Pw == 7 && s == 1 && d->C <= tc2::kMaxC && d->M <= tc2::kNMax && (L.fine[2] % 4) == 0;
+  if (d->precision == CDL_PREC_TF32 && tc2_geom && getenv("CDL_TC2D") && atoi(getenv("CDL_TC2D")) != 0) {
+    p->tc2_ana = true;
+    p->tc2_Ng = round_up(d->M, 16);
+    p->tc2_smem = tc2::smem_layout(d->C, p->tc2_Ng).total;
+    p->precision_eff = CDL_PREC_TF32;
+  }
+
   // ---- CUDA-core analysis configuration ----
   const int mb = ceil_div(g.M, 32);
   p->MBT = (mb <= 1) ? 1 : (mb <= 2) ? 2 : (mb <= 4) ? 4 : (mb <= 6) ? 6 : 8;
@@ -362,6 +392,19 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
       return CDL_CUDA_ERROR_BASE + (int)e;
     }
   }
+  if (p->tc2_ana) {
+    { int rc = load_encode_tiled(); if (rc) { cdl_plan_destroy(p); return rc; } }
+    int dev_sms = 0;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device);
+    p->sm_count = dev_sms;
+    p->wA2_layer = (size_t)tc2::kP * g.C * p->tc2_Ng * 8;
+    if ((e = cudaMalloc(&p->wA2, p->wA2_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc2::smem_layout(tc2::kMaxC, tc2::kNMax).total)) != cudaSuccess) {   // the limit is per function, not per plan
+      cdl_plan_destroy(p);
+      return CDL_CUDA_ERROR_BASE + (int)e;
+    }
+  }
   if ((e = cudaFuncSetAttribute((const void*)p->ana_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ana_smem)) != cudaSuccess ||
       (e = cudaFuncSetAttribute((const void*)p->syn_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->syn_smem)) != cudaSuccess) {
     cdl_plan_destroy(p);
@@ -406,6 +449,7 @@ extern "C" void cdl_plan_destroy(cdl_plan_t* p) {
   if (p->wAtc) cudaFree(p->wAtc);
   if (p->wBtc) cudaFree(p->wBtc);
   if (p->wBtc_lo) cudaFree(p->wBtc_lo);
+  if (p->wA2) cudaFree(p->wA2);
   delete p;
 }
 
@@ -501,6 +545,10 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
         tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
         CDL_LAUNCH_CHECK(p);
       }
+    }
+    if (p->tc2_ana) {
+      tc2::k_pack_tc2_analysis<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
+      CDL_LAUNCH_CHECK(p);
     }
   }
   CDL_CUDA(cudaMemcpyAsync(p->t, t, (size_t)g.K * 2 * g.M * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -617,6 +665,27 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     { int rc = make_fine_tmap(&rmap0, rr, p->g, p->g.Fw); if (rc) return rc; }
     { int rc = make_fine_tmap(&rmap1, rs, p->g, p->g.Fw + 4); if (rc) return rc; }
     tc::k_tc_analysis<<<2 * pairs, tc::kAThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a, rmap0, rmap1);
+    CDL_LAUNCH_CHECK(p);
+    return CDL_OK;
+  }
+  if (p->tc2_ana) {
+    tc2::Ana2Params a;
+    a.N = p->g.N; a.C = p->g.C; a.M = p->g.M; a.H = p->g.Fh; a.W = p->g.Fw;
+    a.Ng = p->tc2_Ng;
+    a.z = z;
+    a.wpack = p->wA2 + (size_t)k * p->wA2_layer;
+    a.t0 = p->t + (size_t)k * 2 * p->g.M;
+    a.t1 = a.t0 + p->g.M;
+    a.cvec = c;
+    a.first = first ? 1 : 0;
+    a.tiles_w = ceil_div(p->g.Fw, tc2::kTW);
+    a.tiles_h = ceil_div(p->g.Fh, tc2::kTH);
+    a.ntiles = p->g.N * a.tiles_h * a.tiles_w;
+    int ctas = p->sm_count;
+    if (ctas > a.ntiles) ctas = a.ntiles;
+    CUtensorMap rmap;
+    { int rc = make_tmap2d(&rmap, r, p->g); if (rc) return rc; }
+    tc2::k_tc2_analysis<<<ctas, tc2::kThreads, p->tc2_smem, (cudaStream_t)stream_>>>(a, rmap);
     CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }

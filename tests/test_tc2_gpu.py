@@ -1,0 +1,87 @@
+"""Bring-up tests of the EXPERIMENTAL 2-D tensor-core analysis kernel (csrc/cdl_tc2_analysis.cuh, CDL_TC2D=1).
+
+Opt-in: the kernel was written at the end of round 1 with no GPU time left, so these tests only run with
+CDL_RUN_EXPERIMENTAL=1 (scripts/gpu_tc2.sh); the default `-m gpu` suite never routes through it.
+The first test uses small-integer data, exactly representable in tf32 with exact fp32 sums: the tensor-core step must
+then equal the exact fp32 CUDA-core step BIT FOR BIT, so any difference is an indexing error, not rounding."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CDL_RUN_EXPERIMENTAL") != "1", reason="experimental 2-D tcgen05 path: set CDL_RUN_EXPERIMENTAL=1")]
+
+
+def _plans(N, C, M, K, H, W):
+    from cdlnet_video_b200 import Plan
+    os.environ.pop("CDL_TC2D", None)
+    ref = Plan(2, N, C, M, K, (H, W), (7, 7), 1, precision="fp32")
+    os.environ["CDL_TC2D"] = "1"
+    try:
+        tc = Plan(2, N, C, M, K, (H, W), (7, 7), 1, precision="tf32")
+    finally:
+        os.environ.pop("CDL_TC2D", None)
+    assert ref.precision == "fp32" and tc.precision == "tf32"
+    return ref, tc
+
+
+@pytest.mark.parametrize("N,C,M,H,W", [(2, 3, 64, 40, 72), (1, 3, 20, 21, 44), (3, 2, 64, 128, 256), (1, 1, 32, 16, 32)])
+def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
+    torch.manual_seed(N * 100 + C * 10 + M)
+    dev = torch.device("cuda", 0)
+    K = 2
+    ref, tc = _plans(N, C, M, K, H, W)
+    A = [torch.randint(-4, 5, (M, C, 7, 7), device=dev).float() / 8 for _ in range(K)]
+    t = torch.randint(0, 4, (K, 2, M), device=dev).float() / 4
+    for pl in (ref, tc):
+        pl.set_weights(A, A, t)
+    r = torch.randint(-4, 5, (N, C, H, W), device=dev).float()
+    c = torch.tensor([0.25 * (n + 1) for n in range(N)], device=dev)
+    z0 = torch.randint(-8, 9, (N, M, H, W), device=dev).float()
+    for first in (True, False):
+        for k in range(K):
+            za, zb = z0.clone(), z0.clone()
+            ref.analysis_step(k, r, za, c=c, first=first)
+            tc.analysis_step(k, r, zb, c=c, first=first)
+            torch.cuda.synchronize()
+            bad = (za != zb)
+            if bad.any():                                   # where the mismatches sit tells which index map is wrong
+                b = bad.float()
+                by_res = [round(b[..., i::4].mean().item(), 3) for i in range(4)]           # w mod 4 = residue / accumulator
+                by_row = [round(b[:, :, i::16].mean().item(), 3) for i in range(16)]         # h mod 16 = tile row
+                by_blk = [round(b[:, i:i + 8].mean().item(), 3) for i in range(0, M, 8)]     # 8-subband block
+                by_col = [round(b[..., i::32].mean().item(), 3) for i in range(0, 32, 4)]    # lane i (w mod 32, residue 0)
+                idx = bad.nonzero()[:4].tolist()
+                vals = [(za[tuple(i)].item(), zb[tuple(i)].item()) for i in idx]
+                pytest.fail(f"first={first} k={k} bad={int(bad.sum())}/{bad.numel()} res={by_res} row={by_row} blk={by_blk} col={by_col} at={idx} ref/tc={vals}")
+
+
+def test_forward_parity_vs_oracle_cfg1b_like():
+    """CDLNet(K=20, M=32, P=7, s=1) (root args.json, SURVEY cfg 1b) on a small image: max|xhat - oracle| <= 1e-4."""
+    import cdl_oracle as O
+    import cdlnet_video_b200 as cb
+    torch.manual_seed(3)
+    K, M = 20, 32
+    net = cb.CDLNet(K=K, M=M, P=7, s=1, C=1, adaptive=True, init=False)
+    with torch.no_grad():
+        for k in range(K):
+            net.A[k].weight.mul_(0.05)
+            net.B[k].weight.copy_(net.A[k].weight * (1 + 0.05 * torch.randn_like(net.A[k].weight)))
+        net.t.copy_(torch.rand_like(net.t) * 0.01)
+    y = torch.rand(2, 1, 64, 96)
+    xr, zr, *_ = O.forward_t(y, [m.weight.detach() for m in net.A], [m.weight.detach() for m in net.B], net.t.detach(), 1, 25.0, True, 1)
+    net = net.cuda().eval()
+    net.precision = "tf32"
+    os.environ["CDL_TC2D"] = "1"
+    try:
+        with torch.no_grad():
+            xhat, z = net(y.cuda(), 25.0)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("CDL_TC2D", None)
+    plan = next(reversed(net._plans.values()))
+    assert plan.precision == "tf32"
+    ex = (xhat.cpu() - xr).abs().max().item()
+    print(f"tc2 forward: max|xhat-oracle|={ex:.3e} max|z-oracle|={(z.cpu() - zr).abs().max().item():.3e}")
+    assert ex <= 1e-4, ex
