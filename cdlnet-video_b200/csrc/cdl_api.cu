@@ -16,6 +16,7 @@
 #include "cdl_tc_analysis.cuh"
 #include "cdl_tc_synthesis.cuh"
 #include "cdl_tc2_analysis.cuh"
+#include "cdl_tc2_synthesis.cuh"
 
 using namespace cdl;
 
@@ -111,6 +112,9 @@ struct cdl_plan {
   float* wA2;          // [K][7*C][Ng*8] tf32 filters in UMMA layout
   size_t wA2_layer;
   size_t tc2_smem;
+  bool tc2_syn;        // residual synthesis on the tensor cores too (cdl_tc2_synthesis.cuh); CDL_TC2D=2
+  float* wB2;          // [K][Ng/8][176*8] tf32 filters in UMMA layout
+  size_t wB2_layer;
   int sm_count;
   bool have_weights;
   // cdl_forward only: the analysis step's rounding pass re-arms the residual buffer with -yp for the next synthesis
@@ -300,6 +304,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   const bool tc2_geom = !nd3 && Ph == 7 && Pw == 7 && s == 1 && d->C <= tc2::kMaxC && d->M <= tc2::kNMax && (L.fine[2] % 4) == 0;
   if (d->precision == CDL_PREC_TF32 && tc2_geom && getenv("CDL_TC2D") && atoi(getenv("CDL_TC2D")) != 0) {
     p->tc2_ana = true;
+    p->tc2_syn = atoi(getenv("CDL_TC2D")) >= 2;
     p->tc2_Ng = round_up(d->M, 16);
     p->tc2_smem = tc2::smem_layout(d->C, p->tc2_Ng).total;
     p->precision_eff = CDL_PREC_TF32;
@@ -398,7 +403,11 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device);
     p->sm_count = dev_sms;
     p->wA2_layer = (size_t)tc2::kP * g.C * p->tc2_Ng * 8;
+    p->wB2_layer = (size_t)(p->tc2_Ng / 8) * tc2::kSN * 8;
     if ((e = cudaMalloc(&p->wA2, p->wA2_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&p->wB2, p->wB2_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc2::syn_smem_bytes(tc2::kNMax))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::smem_layout(tc2::kMaxC, tc2::kNMax).total)) != cudaSuccess) {   // the limit is per function, not per plan
       cdl_plan_destroy(p);
@@ -450,6 +459,7 @@ extern "C" void cdl_plan_destroy(cdl_plan_t* p) {
   if (p->wBtc) cudaFree(p->wBtc);
   if (p->wBtc_lo) cudaFree(p->wBtc_lo);
   if (p->wA2) cudaFree(p->wA2);
+  if (p->wB2) cudaFree(p->wB2);
   delete p;
 }
 
@@ -548,6 +558,8 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
     }
     if (p->tc2_ana) {
       tc2::k_pack_tc2_analysis<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
+      CDL_LAUNCH_CHECK(p);
+      tc2::k_pack_tc2_synthesis<<<32, 256, 0, st>>>(B[k], p->wB2 + (size_t)k * p->wB2_layer, g.M, g.C, p->tc2_Ng);
       CDL_LAUNCH_CHECK(p);
     }
   }
@@ -765,6 +777,29 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
       tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
       CDL_LAUNCH_CHECK(p);
     }
+    return CDL_OK;
+  }
+  if (p->tc2_syn && residual) {
+    // residual synthesis of the 2-D stride-1 networks on the tensor cores; the final D z (residual == 0) stays on the
+    // exact fp32 kernel below: its rounding would land directly on xhat
+    cudaStream_t st = (cudaStream_t)stream_;
+    const long long n4 = (long long)p->g.N * p->g.C * p->g.fine_vol() / 4;
+    long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+    tc::k_neg_copy<<<(int)blocks, 256, 0, st>>>(yp, out, n4);          // out <- -yp ; the scatter-add completes mask * B z - yp
+    CDL_LAUNCH_CHECK(p);
+    tc2::Syn2Params a;
+    a.N = p->g.N; a.C = p->g.C; a.M = p->g.M; a.H = p->g.Fh; a.W = p->g.Fw;
+    a.Kg = p->tc2_Ng;
+    a.z = z; a.out = out;
+    a.mask = p->desc.has_mask ? mask_p : nullptr;
+    a.wpack = p->wB2 + (size_t)k * p->wB2_layer;
+    a.tiles_w = ceil_div(p->g.Fw, tc2::kSTW);
+    a.tiles_h = ceil_div(p->g.Fh, tc2::kSTH);
+    a.ntiles = p->g.N * a.tiles_h * a.tiles_w;
+    int ctas = p->sm_count;
+    if (ctas > a.ntiles) ctas = a.ntiles;
+    tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
+    CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }
   SynParams s = p->syn_cfg;

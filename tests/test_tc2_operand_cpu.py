@@ -134,3 +134,80 @@ def test_shared_memory_budget():
     total = stage + 2 * a128(C * ROWS * SW * 4) + 2 * 64 * 4 + 128
     assert total == 43008 + 76032 + 2 * 10624 + 512 + 128
     assert total < 200 * 1024
+
+
+# ------------------------------------------------------------------------------------------------------------
+# residual synthesis (cdl_tc2_synthesis.cuh): GEMM + col2im
+# ------------------------------------------------------------------------------------------------------------
+SHDR = os.path.join(os.path.dirname(HDR), "cdl_tc2_synthesis.cuh")
+SSRC = open(SHDR).read()
+
+
+def test_synthesis_constants_and_lockstep():
+    assert "constexpr int kSTH = 4, kSTW = 32;" in SSRC and "constexpr int kSN = 176;" in SSRC
+    assert "const int th = (t + r) % kP;" in SSRC
+    assert "float* row = sX + (c * kFY + r + th) * kFPitch + lane;" in SSRC
+    assert "const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;" in SSRC
+    # at every step the four col2im warps (tile rows r) write four DIFFERENT footprint rows r + th
+    for t in range(7):
+        rows = [r + (t + r) % 7 for r in range(4)]
+        assert len(set(rows)) == 4 and max(rows) <= 9
+    # and every warp visits every th exactly once
+    for r in range(4):
+        assert sorted((t + r) % 7 for t in range(7)) == list(range(7))
+    # TMEM budget: two accumulators + two A slots
+    assert 2 * 176 + 2 * 64 <= 512
+
+
+def _pack_syn(w, Kg):
+    """k_pack_tc2_synthesis: ConvTranspose2d weight (M,C,7,7) -> [Kg/8 k-steps][22 groups][2][8][4]."""
+    M, C = w.shape[:2]
+    out = np.zeros((Kg // 8) * 176 * 8, w.dtype)
+    for i in range(out.size):
+        e, r8, kc, grp, ks = i % 4, (i // 4) % 8, (i // 32) % 2, (i // 64) % 22, i // (176 * 8)
+        n, m = grp * 8 + r8, ks * 8 + kc * 4 + e
+        row, tw = n >> 3, n & 7
+        c, th = row // 7, row % 7
+        if row < 7 * C and tw < 7 and m < M:
+            out[i] = w[m, c, th, tw]
+    return out
+
+
+@pytest.mark.parametrize("C,M,H,W", [(1, 32, 9, 40), (3, 64, 12, 72), (3, 20, 7, 44)])
+def test_synthesis_gemm_col2im_equals_conv_transpose2d(C, M, H, W):
+    rng = np.random.default_rng(C * 100 + M)
+    z = rng.integers(-4, 5, size=(M, H, W)).astype(np.float32)
+    w = rng.integers(-4, 5, size=(M, C, 7, 7)).astype(np.float32)
+    want = torch.nn.functional.conv_transpose2d(torch.from_numpy(z)[None], torch.from_numpy(w), padding=3)[0].numpy()
+    Kg = (M + 15) // 16 * 16
+    pack = _pack_syn(w, Kg)
+    out = np.zeros((C, H, W), np.float32)
+    for h0 in range(0, H, 4):
+        for w0 in range(0, W, 32):
+            A = np.zeros((128, Kg), np.float32)                 # TMEM A slot: lane = 32*row + w, column = subband
+            for lane in range(128):
+                r, x = divmod(lane, 32)
+                if h0 + r < H and w0 + x < W:
+                    A[lane, :M] = z[:, h0 + r, w0 + x]
+            D = np.zeros((128, 176), np.float32)
+            for ks in range(Kg // 8):                           # B descriptor: start + ks*176*32 B, LBO 128 B, SBO 256 B
+                Bm = np.zeros((176, 8), np.float32)
+                for n in range(176):
+                    for j in range(8):
+                        Bm[n, j] = pack[ks * 176 * 8 + (n // 8) * 64 + (j // 4) * 32 + (n % 8) * 4 + (j % 4)]
+                D += A[:, 8 * ks:8 * ks + 8] @ Bm.T
+            fp = np.zeros((C, 10, 40), np.float32)              # col2im into the footprint, then the flush
+            for r in range(4):
+                for c in range(C):
+                    for t in range(7):
+                        th = (t + r) % 7
+                        for lane in range(32):
+                            v = D[32 * r + lane, (c * 7 + th) * 8:(c * 7 + th) * 8 + 8]
+                            fp[c, r + th, lane:lane + 7] += v[:7]
+            for c in range(C):
+                for y in range(10):
+                    for x in range(38):
+                        gh, gw = h0 - 3 + y, w0 - 3 + x
+                        if 0 <= gh < H and 0 <= gw < W:
+                            out[c, gh, gw] += fp[c, y, x]
+    assert np.array_equal(out, want)
