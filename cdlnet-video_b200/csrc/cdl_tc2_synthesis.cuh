@@ -17,8 +17,9 @@
 //   * Accumulators double buffered: 2 x 176 + 2 x 64 = 480 of 512 TMEM columns.
 //   * col2im (4 warps = the 4 tile rows): the (c,th) rows are walked in lock step - at step t warp r handles
 //     th = (t + r) mod 7, which lands on footprint row r + th = t + 2r (- 7 when wrapped): distinct for the four
-//     warps (tests/test_tc2_operand_cpu.py), a named barrier between steps - no shared-memory atomics.  Each lane adds
-//     its 7 tw values to 7 consecutive columns of the footprint row (lanes = consecutive columns: conflict-free).
+//     warps (tests/test_tc2_operand_cpu.py), a named barrier between steps - no shared-memory atomics.  Inside a warp
+//     the 7 tw values are combined across lanes with rotate-shuffles, so that every footprint column is
+//     read-modify-written by exactly one lane (own column L, lanes 0..5 also the spill column 32 + L).
 //     The finished 10 x 38 x C footprint is added to `out` with red.global.add (times the mask in JDD mode) and cleared.
 //   * Only the RESIDUAL synthesis runs here; the final dictionary synthesis D z (its rounding would land directly on
 //     xhat) stays on the exact fp32 CUDA-core kernel.
@@ -183,9 +184,19 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
             if (lane == 0) mbar_arrive(&dempty[b]);
           }
           named_bar_sync(2, 32 * kSColWarps);    // lock step: the four warps are on four different footprint rows
-          float* row = sX + (c * kFY + r + th) * kFPitch + lane;
+          // Column x of the footprint row collects tap tw of lane x - tw.  A lane must not read-modify-write columns its
+          // neighbours also touch (no ordering between lanes), so the 7 taps are first combined across lanes with
+          // rotate-shuffles: lane L receives tap tw of lane (L - tw) mod 32 - for L >= tw that is a contribution to its
+          // own column L, for L < tw it comes from lane 32 + L - tw and belongs to the spill column 32 + L.
+          float own = __uint_as_float(v[0]), spill = 0.0f;
 #pragma unroll
-          for (int tw = 0; tw < kP; ++tw) row[tw] += __uint_as_float(v[tw]);
+          for (int tw = 1; tw < kP; ++tw) {
+            const float w = __shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);
+            if (lane >= tw) own += w; else spill += w;
+          }
+          float* row = sX + (c * kFY + r + th) * kFPitch;
+          row[lane] += own;                                   // every column is touched by exactly one lane
+          if (lane < kP - 1) row[32 + lane] += spill;
         }
       }
       named_bar_sync(2, 32 * kSColWarps);        // footprint complete

@@ -146,7 +146,9 @@ SSRC = open(SHDR).read()
 def test_synthesis_constants_and_lockstep():
     assert "constexpr int kSTH = 4, kSTW = 32;" in SSRC and "constexpr int kSN = 176;" in SSRC
     assert "const int th = (t + r) % kP;" in SSRC
-    assert "float* row = sX + (c * kFY + r + th) * kFPitch + lane;" in SSRC
+    assert "float* row = sX + (c * kFY + r + th) * kFPitch;" in SSRC
+    assert "__shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);" in SSRC
+    assert "if (lane >= tw) own += w; else spill += w;" in SSRC and "if (lane < kP - 1) row[32 + lane] += spill;" in SSRC
     assert "const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;" in SSRC
     # at every step the four col2im warps (tile rows r) write four DIFFERENT footprint rows r + th
     for t in range(7):
@@ -201,9 +203,14 @@ def test_synthesis_gemm_col2im_equals_conv_transpose2d(C, M, H, W):
                 for c in range(C):
                     for t in range(7):
                         th = (t + r) % 7
-                        for lane in range(32):
-                            v = D[32 * r + lane, (c * 7 + th) * 8:(c * 7 + th) * 8 + 8]
-                            fp[c, r + th, lane:lane + 7] += v[:7]
+                        v = D[32 * r:32 * r + 32, (c * 7 + th) * 8:(c * 7 + th) * 8 + 8]     # [lane][tw]
+                        own, spill = v[:, 0].copy(), np.zeros(32, np.float32)
+                        for tw in range(1, 7):                  # rotate-shuffle: lane L receives tap tw of lane (L - tw) & 31
+                            w_ = v[(np.arange(32) - tw) & 31, tw]
+                            own += np.where(np.arange(32) >= tw, w_, 0)
+                            spill += np.where(np.arange(32) < tw, w_, 0)
+                        fp[c, r + th, :32] += own
+                        fp[c, r + th, 32:38] += spill[:6]
             for c in range(C):
                 for y in range(10):
                     for x in range(38):
