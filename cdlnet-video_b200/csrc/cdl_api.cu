@@ -112,7 +112,8 @@ struct cdl_plan {
   float* wA2;          // [K][7*C][Ng*8] tf32 filters in UMMA layout
   size_t wA2_layer;
   size_t tc2_smem;
-  bool tc2_syn;        // residual synthesis on the tensor cores too (cdl_tc2_synthesis.cuh); CDL_TC2D=2
+  bool tc2_syn;        // residual synthesis on the tensor cores too (cdl_tc2_synthesis.cuh)
+  bool tc2_maskpass;   // JDD mask applied by an image pass after the scatter-add instead of inside the footprint flush
   float* wB2;          // [K][Ng/8][176*8] tf32 filters in UMMA layout
   size_t wB2_layer;
   int sm_count;
@@ -302,9 +303,12 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
 
   // experimental 2-D tensor-core analysis (the synthesis stays on the fp32 CUDA-core kernel, same planar code layout)
   const bool tc2_geom = !nd3 && Ph == 7 && Pw == 7 && s == 1 && d->C <= tc2::kMaxC && d->M <= tc2::kNMax && (L.fine[2] % 4) == 0;
-  if (d->precision == CDL_PREC_TF32 && tc2_geom && getenv("CDL_TC2D") && atoi(getenv("CDL_TC2D")) != 0) {
+  // CDL_TC2D: 0 = off (fp32 CUDA-core kernels), 1 = tensor-core analysis only, 2 (default) = analysis + residual synthesis
+  const int tc2_mode = getenv("CDL_TC2D") ? atoi(getenv("CDL_TC2D")) : 2;
+  if (d->precision == CDL_PREC_TF32 && tc2_geom && tc2_mode != 0) {
     p->tc2_ana = true;
-    p->tc2_syn = atoi(getenv("CDL_TC2D")) >= 2;
+    p->tc2_syn = tc2_mode >= 2;
+    p->tc2_maskpass = getenv("CDL_TC2D_MASKPASS") ? atoi(getenv("CDL_TC2D_MASKPASS")) != 0 : false;
     p->tc2_Ng = round_up(d->M, 16);
     p->tc2_smem = tc2::smem_layout(d->C, p->tc2_Ng).total;
     p->precision_eff = CDL_PREC_TF32;
@@ -785,13 +789,18 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     cudaStream_t st = (cudaStream_t)stream_;
     const long long n4 = (long long)p->g.N * p->g.C * p->g.fine_vol() / 4;
     long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    tc::k_neg_copy<<<(int)blocks, 256, 0, st>>>(yp, out, n4);          // out <- -yp ; the scatter-add completes mask * B z - yp
-    CDL_LAUNCH_CHECK(p);
+    const bool maskpass = p->desc.has_mask && p->tc2_maskpass;
+    if (maskpass) {
+      CDL_CUDA(cudaMemsetAsync(out, 0, (size_t)n4 * 16, st));            // out <- B z, then one image pass: mask * out - yp
+    } else {
+      tc::k_neg_copy<<<(int)blocks, 256, 0, st>>>(yp, out, n4);        // out <- -yp ; the scatter-add completes mask * B z - yp
+      CDL_LAUNCH_CHECK(p);
+    }
     tc2::Syn2Params a;
     a.N = p->g.N; a.C = p->g.C; a.M = p->g.M; a.H = p->g.Fh; a.W = p->g.Fw;
     a.Kg = p->tc2_Ng;
     a.z = z; a.out = out;
-    a.mask = p->desc.has_mask ? mask_p : nullptr;
+    a.mask = (p->desc.has_mask && !maskpass) ? mask_p : nullptr;
     a.wpack = p->wB2 + (size_t)k * p->wB2_layer;
     a.tiles_w = ceil_div(p->g.Fw, tc2::kSTW);
     a.tiles_h = ceil_div(p->g.Fh, tc2::kSTH);
@@ -800,6 +809,10 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     if (ctas > a.ntiles) ctas = a.ntiles;
     tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
     CDL_LAUNCH_CHECK(p);
+    if (maskpass) {
+      tc2::k_mask_residual<<<(int)blocks, 256, 0, st>>>(out, mask_p, yp, n4);
+      CDL_LAUNCH_CHECK(p);
+    }
     return CDL_OK;
   }
   SynParams s = p->syn_cfg;

@@ -71,6 +71,18 @@ __global__ void k_pack_tc2_synthesis(const float* __restrict__ w, float* __restr
   }
 }
 
+// JDD mode, optional: out <- mask * out - yp as one image pass after the scatter-add (out then starts from zero and the
+// footprint flush needs no mask loads)
+__global__ void __launch_bounds__(256) k_mask_residual(float* out, const float* __restrict__ mask, const float* __restrict__ yp, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(out)[i];
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + i);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(yp) + i);
+    reinterpret_cast<float4*>(out)[i] = make_float4(__fsub_rn(__fmul_rn(m.x, v.x), y.x), __fsub_rn(__fmul_rn(m.y, v.y), y.y),
+                                                    __fsub_rn(__fmul_rn(m.z, v.z), y.z), __fsub_rn(__fmul_rn(m.w, v.w), y.w));
+  }
+}
+
 __device__ __forceinline__ void syn_tile_coords(const Syn2Params& p, int tile, int& n, int& h0, int& w0) {
   const int tw = tile % p.tiles_w; tile /= p.tiles_w;
   const int th = tile % p.tiles_h;

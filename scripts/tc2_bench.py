@@ -48,12 +48,16 @@ def main():
         sigma = 10.0 if use_mask else 25.0
         res = {"config": name, "workload": f"{type(net).__name__}(K={K},M={M},P={P},s={s},C={C}) on {tuple(shape)}"}
         outs = {}
-        for tag, env in (("fp32", None), ("tc2", os.environ.get("TC2_MODE", "2"))):
+        # arms: fp32 = exact CUDA-core kernels (CDL_TC2D=0), tc2 = tensor-core analysis + residual synthesis (the default),
+        # tc2mp = the same with the JDD mask applied by an image pass after the scatter-add (CDL_TC2D_MASKPASS=1)
+        arms = os.environ.get("TC2_ARMS", "fp32,tc2").split(",")
+        for tag in arms:
             net.__dict__.pop("_plans", None)
-            if env:
-                os.environ["CDL_TC2D"] = env
+            os.environ["CDL_TC2D"] = "0" if tag == "fp32" else "2"
+            if tag == "tc2mp":
+                os.environ["CDL_TC2D_MASKPASS"] = "1"
             else:
-                os.environ.pop("CDL_TC2D", None)
+                os.environ.pop("CDL_TC2D_MASKPASS", None)
 
             def fwd():
                 with torch.no_grad():
@@ -77,11 +81,13 @@ def main():
             res[f"{tag}_synthesis_GBs"] = z.numel() * 4 / (sms * 1e-3) / 1e9
             del zz, r, yp, mp
         os.environ.pop("CDL_TC2D", None)
-        res["max_abs_xhat_tc2_vs_fp32"] = (outs["tc2"][0] - outs["fp32"][0]).abs().max().item()
-        res["z_nonzero_frac"] = outs["fp32"][1]
+        os.environ.pop("CDL_TC2D_MASKPASS", None)
         vox = shape[0] * shape[2] * shape[3]
-        res["fp32_Mpix_s"] = vox / (res["fp32_forward_ms"] * 1e-3) / 1e6
-        res["tc2_Mpix_s"] = vox / (res["tc2_forward_ms"] * 1e-3) / 1e6
+        for tag in arms:
+            res[f"{tag}_Mpix_s"] = vox / (res[f"{tag}_forward_ms"] * 1e-3) / 1e6
+            if tag != arms[0]:
+                res[f"max_abs_xhat_{tag}_vs_{arms[0]}"] = (outs[tag][0] - outs[arms[0]][0]).abs().max().item()
+        res["z_nonzero_frac"] = outs[arms[0]][1]
         print(json.dumps(res), flush=True)
         log.write(json.dumps(res) + "\n"); log.flush()
         del net, y, mask, outs

@@ -1,27 +1,32 @@
-"""Bring-up tests of the EXPERIMENTAL 2-D tensor-core analysis kernel (csrc/cdl_tc2_analysis.cuh, CDL_TC2D=1).
+"""The tensor-core kernels of the 2-D stride-1 networks (csrc/cdl_tc2_analysis.cuh, cdl_tc2_synthesis.cuh; BASELINE
+configs 1b, 3, 4) against the exact fp32 CUDA-core kernels and the oracle.
 
-Opt-in: the kernel was written at the end of round 1 with no GPU time left, so these tests only run with
-CDL_RUN_EXPERIMENTAL=1 (scripts/gpu_tc2.sh); the default `-m gpu` suite never routes through it.
-The first test uses small-integer data, exactly representable in tf32 with exact fp32 sums: the tensor-core step must
-then equal the exact fp32 CUDA-core step BIT FOR BIT, so any difference is an indexing error, not rounding."""
+The step tests use small-integer data, exactly representable in tf32 with exact fp32 sums: the tensor-core step must
+then equal the exact fp32 CUDA-core step BIT FOR BIT, so any difference is an indexing error, not rounding.
+CDL_TC2D selects the family at plan creation: 0 = fp32 kernels, 1 = tensor-core analysis only, 2 (default) = analysis +
+residual synthesis."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CDL_RUN_EXPERIMENTAL") != "1", reason="experimental 2-D tcgen05 path: set CDL_RUN_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
+experimental = pytest.mark.skipif(os.environ.get("CDL_RUN_EXPERIMENTAL") != "1", reason="opt-in variant: set CDL_RUN_EXPERIMENTAL=1")
 
 
-def _plans(N, C, M, K, H, W, mode="1", has_mask=False):
+def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=False):
     from cdlnet_video_b200 import Plan
     os.environ.pop("CDL_TC2D", None)
     ref = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="fp32")
-    os.environ["CDL_TC2D"] = mode
+    if mode is not None:
+        os.environ["CDL_TC2D"] = mode
+    if maskpass:
+        os.environ["CDL_TC2D_MASKPASS"] = "1"
     try:
         tc = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="tf32")
     finally:
         os.environ.pop("CDL_TC2D", None)
+        os.environ.pop("CDL_TC2D_MASKPASS", None)
     assert ref.precision == "fp32" and tc.precision == "tf32"
     return ref, tc
 
@@ -31,7 +36,7 @@ def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
     torch.manual_seed(N * 100 + C * 10 + M)
     dev = torch.device("cuda", 0)
     K = 2
-    ref, tc = _plans(N, C, M, K, H, W)
+    ref, tc = _plans(N, C, M, K, H, W, mode="1")
     A = [torch.randint(-4, 5, (M, C, 7, 7), device=dev).float() / 8 for _ in range(K)]
     t = torch.randint(0, 4, (K, 2, M), device=dev).float() / 4
     for pl in (ref, tc):
@@ -57,13 +62,15 @@ def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
                 pytest.fail(f"first={first} k={k} bad={int(bad.sum())}/{bad.numel()} res={by_res} row={by_row} blk={by_blk} col={by_col} at={idx} ref/tc={vals}")
 
 
-@pytest.mark.parametrize("N,C,M,H,W,use_mask", [(2, 3, 64, 40, 72, True), (1, 3, 20, 21, 44, False), (3, 2, 64, 128, 256, False), (1, 1, 32, 16, 32, False)])
-def test_synthesis_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask):
-    """Residual synthesis mask * B z - yp on the tensor cores (CDL_TC2D=2) vs the exact fp32 kernel, exact data."""
+@pytest.mark.parametrize("N,C,M,H,W,use_mask,maskpass", [
+    (2, 3, 64, 40, 72, True, False), (1, 3, 20, 21, 44, False, False), (3, 2, 64, 128, 256, False, False), (1, 1, 32, 16, 32, False, False),
+    pytest.param(2, 3, 64, 40, 72, True, True, marks=experimental), pytest.param(1, 3, 48, 64, 128, True, True, marks=experimental)])
+def test_synthesis_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask, maskpass):
+    """Residual synthesis mask * B z - yp on the tensor cores (default family) vs the exact fp32 kernel, exact data."""
     torch.manual_seed(N * 100 + C * 10 + M + 1)
     dev = torch.device("cuda", 0)
     K = 2
-    ref, tc = _plans(N, C, M, K, H, W, mode="2", has_mask=use_mask)
+    ref, tc = _plans(N, C, M, K, H, W, has_mask=use_mask, maskpass=maskpass)
     Bw = [torch.randint(-4, 5, (M, C, 7, 7), device=dev).float() / 8 for _ in range(K)]
     t = torch.zeros(K, 2, M, device=dev)
     for pl in (ref, tc):
@@ -88,7 +95,7 @@ def test_synthesis_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask
             pytest.fail(f"k={k} bad={int(bad.sum())}/{bad.numel()} row={by_row} col={by_col} c={by_c} at={idx} ref/tc={vals}")
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", None])
 def test_forward_parity_vs_oracle_cfg1b_like(mode):
     """CDLNet(K=20, M=32, P=7, s=1) (root args.json, SURVEY cfg 1b) on a small image: max|xhat - oracle| <= 1e-4."""
     import cdl_oracle as O
@@ -105,7 +112,8 @@ def test_forward_parity_vs_oracle_cfg1b_like(mode):
     xr, zr, *_ = O.forward_t(y, [m.weight.detach() for m in net.A], [m.weight.detach() for m in net.B], net.t.detach(), 1, 25.0, True, 1)
     net = net.cuda().eval()
     net.precision = "tf32"
-    os.environ["CDL_TC2D"] = mode
+    if mode is not None:
+        os.environ["CDL_TC2D"] = mode
     try:
         with torch.no_grad():
             xhat, z = net(y.cuda(), 25.0)
