@@ -11,17 +11,16 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-experimental = pytest.mark.skipif(os.environ.get("CDL_RUN_EXPERIMENTAL") != "1", reason="opt-in variant: set CDL_RUN_EXPERIMENTAL=1")
 
 
-def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=False):
+def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None):
     from cdlnet_video_b200 import Plan
     os.environ.pop("CDL_TC2D", None)
     ref = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="fp32")
     if mode is not None:
         os.environ["CDL_TC2D"] = mode
-    if maskpass:
-        os.environ["CDL_TC2D_MASKPASS"] = "1"
+    if maskpass is not None:
+        os.environ["CDL_TC2D_MASKPASS"] = "1" if maskpass else "0"
     try:
         tc = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="tf32")
     finally:
@@ -31,7 +30,7 @@ def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=False):
     return ref, tc
 
 
-@pytest.mark.parametrize("N,C,M,H,W", [(2, 3, 64, 40, 72), (1, 3, 20, 21, 44), (3, 2, 64, 128, 256), (1, 1, 32, 16, 32)])
+@pytest.mark.parametrize("N,C,M,H,W", [(2, 3, 64, 40, 72), (1, 3, 20, 21, 44), (3, 2, 64, 128, 256), (1, 1, 32, 16, 32), (1, 1, 8, 16, 16), (2, 3, 48, 33, 100)])
 def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
     torch.manual_seed(N * 100 + C * 10 + M)
     dev = torch.device("cuda", 0)
@@ -63,8 +62,10 @@ def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
 
 
 @pytest.mark.parametrize("N,C,M,H,W,use_mask,maskpass", [
-    (2, 3, 64, 40, 72, True, False), (1, 3, 20, 21, 44, False, False), (3, 2, 64, 128, 256, False, False), (1, 1, 32, 16, 32, False, False),
-    pytest.param(2, 3, 64, 40, 72, True, True, marks=experimental), pytest.param(1, 3, 48, 64, 128, True, True, marks=experimental)])
+    (2, 3, 64, 40, 72, True, None), (1, 3, 20, 21, 44, False, None), (3, 2, 64, 128, 256, False, None), (1, 1, 32, 16, 32, False, None),
+    (1, 1, 8, 16, 16, False, None),
+    (2, 3, 64, 40, 72, True, True), (1, 3, 48, 64, 128, True, True),       # JDD mask as an image pass (the default) ...
+    (2, 3, 64, 40, 72, True, False), (1, 3, 48, 64, 128, True, False)])    # ... or inside the footprint flush (CDL_TC2D_MASKPASS=0)
 def test_synthesis_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask, maskpass):
     """Residual synthesis mask * B z - yp on the tensor cores (default family) vs the exact fp32 kernel, exact data."""
     torch.manual_seed(N * 100 + C * 10 + M + 1)
@@ -124,4 +125,22 @@ def test_forward_parity_vs_oracle_cfg1b_like(mode):
     assert plan.precision == "tf32"
     ex = (xhat.cpu() - xr).abs().max().item()
     print(f"tc2 forward (CDL_TC2D={mode}): max|xhat-oracle|={ex:.3e} max|z-oracle|={(z.cpu() - zr).abs().max().item():.3e}")
+    assert ex <= 1e-4, ex
+
+
+def test_golden_fixture_2d_stride1_auto():
+    """The reference-generated golden vector of the 2-D stride-1 network (sigma=None, non-adaptive, M = 8 -> GEMM N = 16)
+    through the default (`auto`) family = the tensor-core kernels: max|xhat - reference| <= 1e-4 (north_star's bar)."""
+    import numpy as np
+    from util import case_inputs, load_case, module_from_case
+    d = load_case("cdlnet2d_nonadaptive")
+    net = module_from_case(d, "cdlnet2d_nonadaptive").cuda()
+    net.precision = "auto"
+    y, sigma, mask = case_inputs(d, torch.device("cuda", 0))
+    with torch.no_grad():
+        xhat, z = net(y, sigma, mask=mask)
+    plan = next(iter(net._plans.values()))
+    assert plan.precision == "tf32" and plan.launch_count() > 0
+    ex = np.abs(xhat.cpu().numpy() - d["xhat"]).max()
+    assert tuple(xhat.shape) == d["xhat"].shape and tuple(z.shape) == d["z"].shape
     assert ex <= 1e-4, ex
