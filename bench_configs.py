@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Secondary measurements: the other BASELINE.json configurations (bench.py keeps the driver contract on config 2).
 
-  python bench_configs.py --config cfg1            # CDLNet-s2030, one 256x256 image           (fp32 kernels)
-  python bench_configs.py --config cfg3            # JDD CDLNet, 32 x 3 x 1024^2 + Bayer mask   (fp32 kernels)
-  python bench_configs.py --config cfg4            # GDLNet colour, 64 x 3 x 512^2              (fp32 kernels)
+  python bench_configs.py --config cfg1            # CDLNet-s2030, one 256x256 image           (fp32 CUDA-core kernels: s = 2)
+  python bench_configs.py --config cfg1b           # CDLNet root args.json, one 256x256 image   (2-D tcgen05 kernels)
+  python bench_configs.py --config cfg3            # JDD CDLNet, 32 x 3 x 1024^2 + Bayer mask   (2-D tcgen05 kernels)
+  python bench_configs.py --config cfg4            # GDLNet colour, 64 x 3 x 512^2              (2-D tcgen05 kernels)
+  (--precision fp32 or CDL_TC2D=0 selects the exact fp32 CUDA-core kernels for the 2-D configurations)
   python bench_configs.py --config cfg5 --frames 240                      # one 1080p clip on 1 GPU (tcgen05 kernels)
   torchrun --nproc-per-node N ... bench_configs.py --config cfg5 --frames 240   # temporally sharded, halo exchange
 
@@ -125,6 +127,7 @@ def main():
         else:
             raise SystemExit("unknown config")
         net = make_net(kind, K, M, P, s, C).to(dev)
+        net.precision = args.precision
         y = torch.rand(*shape, device=dev)
         mask = 1
         if use_mask:                                           # RGGB Bayer mask (reference utils.py:13-19)

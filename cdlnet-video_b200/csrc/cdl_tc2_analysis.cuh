@@ -3,9 +3,12 @@
 //
 //     z <- ST(z - A_k r, t0 + c*t1)            (reference model/net.py:85,87 + :11-14; GDLNet :668,670)
 //
-// EXPERIMENTAL / OPT-IN (CDL_TC2D=1 at plan creation): written at the end of round 1 without GPU time left to run it;
-// the operand construction is modelled and checked on the CPU (tests/test_tc2_operand_cpu.py), the kernel itself has
-// not been executed yet.  Without the switch every 2-D plan keeps the exact fp32 CUDA-core kernels (cdl_cc.cuh).
+// Default for tf32/auto plans of this geometry (CDL_TC2D=0 at plan creation falls back to the exact fp32 CUDA-core
+// kernels of cdl_cc.cuh; fine width must be a multiple of 4).  Bit-exact against the fp32 kernel on exactly
+// representable data, 2-6e-5 on xhat against the oracle / fp32 family (tests/test_tc2_gpu.py, profiles/r01k_*);
+// the operand construction is also modelled on the CPU (tests/test_tc2_operand_cpu.py).
+// Measured (B200, config 3: 32 x 3 x 1024^2, M = 64): 3.38 ms per launch = 5.08 TB/s of code traffic = 78 % of the
+// measured HBM copy bandwidth (fp32 CUDA-core kernel: 20.8 ms).
 //
 // Implicit GEMM  U[q, m] = sum_{c,th,j} R[q, (c,th,j)] * W[m, (c,th,j)],  kind::tf32, fp32 accumulation in TMEM,
 // cta_group::1 (the filter bank is 7*C*64*32 B <= 43 KB, no need to split it over a CTA pair):
@@ -114,7 +117,7 @@ __device__ __forceinline__ void stg128_pred(float* p, const float (&v)[4], int o
 }
 
 // mbarrier wait that cannot hang the device: a hand-off that does not arrive within ~2 s traps (reported by the next
-// CUDA call as a launch failure) - bring-up safety for a kernel that has not run on hardware yet.
+// CUDA call as a launch failure instead of a hung GPU).  The clock is only read every 1024 failed polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
