@@ -17,6 +17,7 @@
 #include "cdl_tc_synthesis.cuh"
 #include "cdl_tc2_analysis.cuh"
 #include "cdl_tc2_synthesis.cuh"
+#include "cdl_tc2_synthesis_v2.cuh"
 
 using namespace cdl;
 
@@ -113,6 +114,7 @@ struct cdl_plan {
   size_t wA2_layer;
   size_t tc2_smem;
   bool tc2_syn;        // residual synthesis on the tensor cores too (cdl_tc2_synthesis.cuh)
+  bool tc2_syn_v2;     // candidate col2im (cdl_tc2_synthesis_v2.cuh), opt-in with CDL_TC2D_SYN=2; not yet validated on hardware
   bool tc2_maskpass;   // JDD mask applied by an image pass after the scatter-add instead of inside the footprint flush
   float* wB2;          // [K][Ng/8][176*8] tf32 filters in UMMA layout
   size_t wB2_layer;
@@ -308,6 +310,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   if (d->precision == CDL_PREC_TF32 && tc2_geom && tc2_mode != 0) {
     p->tc2_ana = true;
     p->tc2_syn = tc2_mode >= 2;
+    p->tc2_syn_v2 = p->tc2_syn && getenv("CDL_TC2D_SYN") && atoi(getenv("CDL_TC2D_SYN")) == 2;
     // JDD mask as one image pass after the scatter-add (default; measured 5.5 vs 10.0 ms per synthesis on config 3) or,
     // with CDL_TC2D_MASKPASS=0, inside the footprint flush
     p->tc2_maskpass = getenv("CDL_TC2D_MASKPASS") ? atoi(getenv("CDL_TC2D_MASKPASS")) != 0 : true;
@@ -414,6 +417,8 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
         (e = cudaMalloc(&p->wB2, p->wB2_layer * g.K * sizeof(float))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::syn_smem_bytes(tc2::kNMax))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc2::syn2_smem_bytes(tc2::kNMax))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::smem_layout(tc2::kMaxC, tc2::kNMax).total)) != cudaSuccess) {   // the limit is per function, not per plan
       cdl_plan_destroy(p);
@@ -809,7 +814,8 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.ntiles = p->g.N * a.tiles_h * a.tiles_w;
     int ctas = p->sm_count;
     if (ctas > a.ntiles) ctas = a.ntiles;
-    tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
+    if (p->tc2_syn_v2) tc2::k_tc2_synthesis_v2<<<ctas, tc2::kSThreads, tc2::syn2_smem_bytes(a.Kg), st>>>(a);
+    else tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
     CDL_LAUNCH_CHECK(p);
     if (maskpass) {
       tc2::k_mask_residual<<<(int)blocks, 256, 0, st>>>(out, mask_p, yp, n4);

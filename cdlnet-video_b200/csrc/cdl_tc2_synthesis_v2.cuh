@@ -1,0 +1,216 @@
+// cdl_tc2_synthesis_v2.cuh — CANDIDATE successor of k_tc2_synthesis (same GEMM, different col2im), OPT-IN with
+// CDL_TC2D_SYN=2 at plan creation.  NOT YET RUN ON HARDWARE: written after the round's GPU budget was spent; its index
+// maps are modelled and checked on the CPU (tests/test_tc2_operand_cpu.py::test_synthesis_v2_*), its GPU tests are
+// gated by CDL_RUN_EXPERIMENTAL=1 (tests/test_tc2_gpu.py).  The default path stays k_tc2_synthesis.
+//
+// Why: k_tc2_synthesis spends ~5700 cycles per 128-site tile against ~760 cycles of MMAs (profiles/r01_configs.md):
+// its four col2im warps walk the 7*C (c,th) rows in lock step - 21 rounds of tcgen05.ld -> wait -> named barrier ->
+// shuffles -> shared-memory read-modify-write, every latency exposed - and then flush and clear the footprint
+// themselves while the tensor pipe idles.
+//
+// What changes:
+//   * WRITE-ONCE PRIVATE FOOTPRINTS.  Warp r (tile row r) owns a private buffer priv[r][(c,th)][40]: row (c,th) of it
+//     receives exactly one value per column and tile (columns 0..31 from the lanes' own sums, 32..37 from the spill
+//     sums of lanes 0..5), so it is WRITTEN, not accumulated: no read-modify-write, no clearing, no ordering between
+//     warps, no lock step, no named barriers.
+//   * The accumulator is drained in 32-column tcgen05.ld's (four (c,th) rows each), the next load in flight while the
+//     current rows are shuffled and stored.
+//   * The overlap-add moves into the flush: out[c, h0-3+y, w0-3+x] += sum_{r = max(0,y-6)}^{min(3,y)} priv[r][c, y-r][x]
+//     (at most 4 terms), executed by the eight PRODUCER warps (idle once their 32 loads and 4 tcgen05.st's per tile are
+//     issued) one tile behind, on a double-buffered priv (2 x 13.4 KB), so the col2im warps start the next tile at once.
+#pragma once
+#include "cdl_tc2_synthesis.cuh"
+
+namespace cdl {
+namespace tc2 {
+
+constexpr int kPrivRows = kMaxC * kP;                       // 21 (c,th) rows per warp
+constexpr int kPrivWarp = kPrivRows * kFPitch;              // floats per warp
+constexpr int kPrivBuf = kSColWarps * kPrivWarp;            // floats per buffer (4 warps)
+
+__host__ __device__ inline uint32_t syn2_smem_bytes(int Kg) {
+  return align128(syn_b_bytes(Kg)) + (uint32_t)(2 * kPrivBuf * 4) + 128u;
+}
+
+__global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis_v2(const Syn2Params p) {
+  using namespace ptx;
+  using tc2::mbar_wait;                        // bounded wait (traps instead of hanging)
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t bbytes = syn_b_bytes(p.Kg);
+  float* sB = reinterpret_cast<float*>(smem_raw);
+  float* sP = reinterpret_cast<float*>(smem_raw + align128(bbytes));                  // [2][4 warps][21][40]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + align128(bbytes) + 2 * kPrivBuf * 4);
+  uint64_t* wbar = bars + 0;
+  uint64_t* afull = bars + 1;                  // [2] producers -> MMA
+  uint64_t* aempty = afull + 2;                // [2] MMA commit -> producers
+  uint64_t* dfull = aempty + 2;                // [2] MMA commit -> col2im
+  uint64_t* dempty = dfull + 2;                // [2] col2im -> MMA
+  uint64_t* xfull = dempty + 2;                // [2] col2im -> producers: private footprints of a tile written
+  uint64_t* xfree = xfull + 2;                 // [2] producers -> col2im: flushed, buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stride = gridDim.x;
+  const int ksteps = p.Kg >> 3;
+  const int nrows = kP * p.C;                  // (c,th) rows in use
+
+  if (tid == 0) {
+    mbar_init(wbar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&afull[i], kSProdWarps); mbar_init(&aempty[i], 1);
+      mbar_init(&dfull[i], 1); mbar_init(&dempty[i], kSColWarps);
+      mbar_init(&xfull[i], kSColWarps); mbar_init(&xfree[i], kSProdWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kSMmaWarp) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(wbar, bbytes);
+    for (uint32_t o = 0; o < bbytes; o += 16384u) {
+      const uint32_t n = (bbytes - o < 16384u) ? (bbytes - o) : 16384u;
+      bulk_g2s(reinterpret_cast<char*>(sB) + o, reinterpret_cast<const char*>(p.wpack) + o, n, wbar);
+    }
+  }
+
+  if (warp < kSProdWarps) {
+    // ============================== producers: code tile -> tf32 -> TMEM A ring; overlap-add + flush ==============================
+    const int quad = warp & 3, half = warp >> 2;
+    const int nh = p.Kg >> 1;
+    const int m0 = half * nh;
+    const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
+    const size_t plane = (size_t)p.H * p.W;
+    float rg[32];
+    auto load_tile = [&](int tile) {
+      int n = 0, h0 = 0, w0 = 0, ok = 0;
+      if (tile < p.ntiles) {
+        syn_tile_coords(p, tile, n, h0, w0);
+        ok = (h0 + quad < p.H) && (w0 + lane < p.W);
+      }
+      const char* base = reinterpret_cast<const char*>(p.z + (((size_t)n * p.M + m0) * p.H + (h0 + quad)) * p.W + (w0 + lane));
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        rg[j] = ldg_f32_pred(base + (size_t)j * plane * 4, ok && j < nh && m0 + j < p.M);
+    };
+    // tile j of this CTA: out[c, h0-3+y, w0-3+x] += sum_r priv[r][c*7 + (y-r)][x]  over the rows r with 0 <= y-r <= 6
+    auto flush_tile = [&](int j) {
+      const int xb = j & 1;
+      int n, h0, w0;
+      syn_tile_coords(p, (int)blockIdx.x + j * stride, n, h0, w0);
+      mbar_wait(&xfull[xb], (j >> 1) & 1);
+      const float* pv = sP + xb * kPrivBuf;
+      const int nf = p.C * kFY * kFX;
+      for (int i = tid; i < nf; i += 32 * kSProdWarps) {
+        const int x = i % kFX, y = (i / kFX) % kFY, c = i / (kFX * kFY);
+        float v = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kSTH; ++r) {
+          const int th = y - r;
+          if (th >= 0 && th < kP) v += pv[r * kPrivWarp + (c * kP + th) * kFPitch + x];
+        }
+        const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;
+        if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
+          const size_t o = (((size_t)n * p.C + c) * p.H + gh) * p.W + gw;
+          if (p.mask) v *= __ldg(p.mask + o);
+          red_add_f32(p.out + o, v);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfree[xb]);
+    };
+    load_tile(blockIdx.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+      const int b = it & 1, u = it >> 1;
+      uint32_t rt[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rt[j] = tf32_rna_bits(rg[j]);
+      load_tile(tile + stride);
+      mbar_wait(&aempty[b], (u & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acol = lane_addr + (uint32_t)(kSColA + b * kNMax + m0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (8 * q < nh) tmem_st8(acol + 8 * q, *reinterpret_cast<const uint32_t(*)[8]>(&rt[8 * q]));
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[b]);
+      if (it > 0) flush_tile(it - 1);            // one tile behind: its col2im ran while this tile's A was produced
+    }
+    if (it > 0) flush_tile(it - 1);
+  } else if (warp < kSMmaWarp) {
+    // ============================== col2im: accumulator -> write-once private footprint ==============================
+    const int r = warp - kSProdWarps;
+    const uint32_t lane_addr = tbase + ((uint32_t)(r * 32) << 16);
+    // one (c,th) row: combine the 7 w-taps across lanes (lane L receives tap tw of lane (L - tw) mod 32: its own column for
+    // L >= tw, the spill column 32 + L otherwise) and WRITE columns L and 32 + L of the private row
+    auto put_row = [&](const uint32_t* v, float* row) {
+      float own = __uint_as_float(v[0]), spill = 0.0f;
+#pragma unroll
+      for (int tw = 1; tw < kP; ++tw) {
+        const float w = __shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);
+        if (lane >= tw) own += w; else spill += w;
+      }
+      row[lane] = own;
+      if (lane < kP - 1) row[32 + lane] = spill;
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+      const int b = it & 1, u = it >> 1;
+      mbar_wait(&xfree[b], (u & 1) ^ 1);         // the flush of tile it-2 has read this private buffer
+      mbar_wait(&dfull[b], u & 1);
+      tc_fence_after();
+      const uint32_t dcol = lane_addr + (uint32_t)(kSColD + b * kSN);
+      float* priv = sP + b * kPrivBuf + r * kPrivWarp;
+      uint32_t ua[32], ub[32];
+      tmem_ld32(dcol, ua);                       // rows 0..3
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {              // groups of four (c,th) rows = 32 accumulator columns
+        uint32_t (&cur)[32] = (g & 1) ? ub : ua;
+        uint32_t (&nxt)[32] = (g & 1) ? ua : ub;
+        if (4 * g < nrows) {                     // warp-uniform
+          tmem_wait_ld();
+          if (g < 4) { if (4 * (g + 1) < nrows) tmem_ld32(dcol + 32 * (g + 1), nxt); }
+          else if (20 < nrows) tmem_ld8(dcol + 160, *reinterpret_cast<uint32_t(*)[8]>(&nxt[0]));   // row 20
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * g + q < nrows) put_row(&cur[8 * q], priv + (4 * g + q) * kFPitch);
+        }
+      }
+      if (20 < nrows) { tmem_wait_ld(); put_row(&ub[0], priv + 20 * kFPitch); }
+      tc_fence_before();                         // accumulator fully read, private footprint written
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&dempty[b]); mbar_arrive(&xfull[b]); }
+    }
+  } else {
+    // ============================== MMA issue: whole warp converged, one elected lane issues ==============================
+    mbar_wait(wbar, 0);
+    const uint32_t idesc = make_idesc_tf32(128, kSN);
+    const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
+    constexpr uint32_t kBStep = (kSN * 32) >> 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+      const int b = it & 1, u = it >> 1;
+      mbar_wait(&dempty[b], (u & 1) ^ 1);
+      mbar_wait(&afull[b], u & 1);
+      tc_fence_after();
+      const uint32_t dcol = tbase + (uint32_t)(kSColD + b * kSN);
+      const uint32_t acol = tbase + (uint32_t)(kSColA + b * kNMax);
+      for (int j = 0; j < ksteps; ++j)
+        mma_tf32_ts_warp<1>(dcol, acol + 8 * j, bdesc0 + (uint64_t)j * kBStep, idesc, j != 0);
+      mma_commit_warp<1>(&aempty[b]);
+      mma_commit_warp<1>(&dfull[b]);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kSMmaWarp) tmem_dealloc<1>(tbase, 512);
+}
+
+}  // namespace tc2
+}  // namespace cdl

@@ -49,15 +49,18 @@ def main():
         res = {"config": name, "workload": f"{type(net).__name__}(K={K},M={M},P={P},s={s},C={C}) on {tuple(shape)}"}
         outs = {}
         # arms: fp32 = exact CUDA-core kernels (CDL_TC2D=0), tc2 = tensor-core analysis + residual synthesis (the default),
-        # tc2mp = the same with the JDD mask applied by an image pass after the scatter-add (CDL_TC2D_MASKPASS=1)
+        # tc2fm = the same with the JDD mask applied inside the footprint flush (CDL_TC2D_MASKPASS=0),
+        # tc2v2 = the candidate col2im of cdl_tc2_synthesis_v2.cuh (CDL_TC2D_SYN=2)
         arms = os.environ.get("TC2_ARMS", "fp32,tc2").split(",")
         for tag in arms:
             net.__dict__.pop("_plans", None)
             os.environ["CDL_TC2D"] = "0" if tag == "fp32" else "2"
-            if tag == "tc2mp":
-                os.environ["CDL_TC2D_MASKPASS"] = "1"
-            else:
-                os.environ.pop("CDL_TC2D_MASKPASS", None)
+            os.environ.pop("CDL_TC2D_MASKPASS", None)
+            os.environ.pop("CDL_TC2D_SYN", None)
+            if tag == "tc2fm":
+                os.environ["CDL_TC2D_MASKPASS"] = "0"
+            if tag == "tc2v2":
+                os.environ["CDL_TC2D_SYN"] = "2"
 
             def fwd():
                 with torch.no_grad():
@@ -82,6 +85,7 @@ def main():
             del zz, r, yp, mp
         os.environ.pop("CDL_TC2D", None)
         os.environ.pop("CDL_TC2D_MASKPASS", None)
+        os.environ.pop("CDL_TC2D_SYN", None)
         vox = shape[0] * shape[2] * shape[3]
         for tag in arms:
             res[f"{tag}_Mpix_s"] = vox / (res[f"{tag}_forward_ms"] * 1e-3) / 1e6

@@ -13,7 +13,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None):
+experimental = pytest.mark.skipif(os.environ.get("CDL_RUN_EXPERIMENTAL") != "1", reason="not yet validated on hardware: set CDL_RUN_EXPERIMENTAL=1")
+
+
+def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None, syn=None):
     from cdlnet_video_b200 import Plan
     os.environ.pop("CDL_TC2D", None)
     ref = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="fp32")
@@ -21,11 +24,14 @@ def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None):
         os.environ["CDL_TC2D"] = mode
     if maskpass is not None:
         os.environ["CDL_TC2D_MASKPASS"] = "1" if maskpass else "0"
+    if syn is not None:
+        os.environ["CDL_TC2D_SYN"] = syn
     try:
         tc = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="tf32")
     finally:
         os.environ.pop("CDL_TC2D", None)
         os.environ.pop("CDL_TC2D_MASKPASS", None)
+        os.environ.pop("CDL_TC2D_SYN", None)
     assert ref.precision == "fp32" and tc.precision == "tf32"
     return ref, tc
 
@@ -68,10 +74,23 @@ def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
     (2, 3, 64, 40, 72, True, False), (1, 3, 48, 64, 128, True, False)])    # ... or inside the footprint flush (CDL_TC2D_MASKPASS=0)
 def test_synthesis_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask, maskpass):
     """Residual synthesis mask * B z - yp on the tensor cores (default family) vs the exact fp32 kernel, exact data."""
+    _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass, None)
+
+
+@experimental
+@pytest.mark.parametrize("N,C,M,H,W,use_mask,maskpass", [
+    (2, 3, 64, 40, 72, True, None), (1, 3, 20, 21, 44, False, None), (3, 2, 64, 128, 256, False, None), (1, 1, 32, 16, 32, False, None),
+    (1, 1, 8, 16, 16, False, None), (1, 3, 48, 64, 128, True, False)])
+def test_synthesis_v2_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask, maskpass):
+    """The candidate col2im (cdl_tc2_synthesis_v2.cuh, CDL_TC2D_SYN=2): same bar as the default kernel."""
+    _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass, "2")
+
+
+def _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass, syn):
     torch.manual_seed(N * 100 + C * 10 + M + 1)
     dev = torch.device("cuda", 0)
     K = 2
-    ref, tc = _plans(N, C, M, K, H, W, has_mask=use_mask, maskpass=maskpass)
+    ref, tc = _plans(N, C, M, K, H, W, has_mask=use_mask, maskpass=maskpass, syn=syn)
     Bw = [torch.randint(-4, 5, (M, C, 7, 7), device=dev).float() / 8 for _ in range(K)]
     t = torch.zeros(K, 2, M, device=dev)
     for pl in (ref, tc):

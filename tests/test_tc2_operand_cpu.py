@@ -218,3 +218,68 @@ def test_synthesis_gemm_col2im_equals_conv_transpose2d(C, M, H, W):
                         if 0 <= gh < H and 0 <= gw < W:
                             out[c, gh, gw] += fp[c, y, x]
     assert np.array_equal(out, want)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# candidate col2im of cdl_tc2_synthesis_v2.cuh: write-once private footprints, overlap-add in the flush
+# ------------------------------------------------------------------------------------------------------------
+V2SRC = open(os.path.join(os.path.dirname(HDR), "cdl_tc2_synthesis_v2.cuh")).read()
+
+
+def test_synthesis_v2_source_matches_model():
+    assert "if (th >= 0 && th < kP) v += pv[r * kPrivWarp + (c * kP + th) * kFPitch + x];" in V2SRC
+    assert "row[lane] = own;" in V2SRC and "if (lane < kP - 1) row[32 + lane] = spill;" in V2SRC
+    assert "put_row(&cur[8 * q], priv + (4 * g + q) * kFPitch);" in V2SRC
+    assert "tmem_ld32(dcol + 32 * (g + 1), nxt);" in V2SRC and "tmem_ld8(dcol + 160," in V2SRC
+    # shared memory: filters + two private buffers + barriers
+    assert 45056 + 2 * 4 * 21 * 40 * 4 + 128 < 100 * 1024
+
+
+@pytest.mark.parametrize("C,M,H,W", [(1, 32, 9, 40), (3, 64, 12, 72), (2, 20, 7, 44)])
+def test_synthesis_v2_private_footprints_equal_conv_transpose2d(C, M, H, W):
+    rng = np.random.default_rng(C * 100 + M + 7)
+    z = rng.integers(-4, 5, size=(M, H, W)).astype(np.float32)
+    w = rng.integers(-4, 5, size=(M, C, 7, 7)).astype(np.float32)
+    want = torch.nn.functional.conv_transpose2d(torch.from_numpy(z)[None], torch.from_numpy(w), padding=3)[0].numpy()
+    nrows = 7 * C
+    out = np.zeros((C, H, W), np.float32)
+    lanes = np.arange(32)
+    for h0 in range(0, H, 4):
+        for w0 in range(0, W, 32):
+            A = np.zeros((128, M), np.float32)
+            for lane in range(128):
+                r, x = divmod(lane, 32)
+                if h0 + r < H and w0 + x < W:
+                    A[lane] = z[:, h0 + r, w0 + x]
+            D = np.zeros((128, 176), np.float32)               # column (c*7 + th)*8 + tw (packing checked above)
+            for c in range(C):
+                for th in range(7):
+                    D[:, (c * 7 + th) * 8:(c * 7 + th) * 8 + 7] = A @ w[:, c, th, :]
+            priv = np.full((4, 21, 40), np.nan, np.float32)     # NaN = never written: the flush must not read such a cell
+            for r in range(4):
+                # the drain order of the kernel: 32-column loads g = 0..4 (rows 4g..4g+3), then row 20
+                rows = [4 * g + q for g in range(5) if 4 * g < nrows for q in range(4) if 4 * g + q < nrows]
+                if 20 < nrows:
+                    rows.append(20)
+                assert rows == list(range(nrows))
+                for R in rows:
+                    v = D[32 * r:32 * r + 32, 8 * R:8 * R + 8]
+                    own, spill = v[:, 0].copy(), np.zeros(32, np.float32)
+                    for tw in range(1, 7):
+                        w_ = v[(lanes - tw) & 31, tw]
+                        own += np.where(lanes >= tw, w_, 0)
+                        spill += np.where(lanes < tw, w_, 0)
+                    priv[r, R, :32] = own
+                    priv[r, R, 32:38] = spill[:6]
+            for c in range(C):                                  # the flush: at most 4 private rows meet in one output row
+                for y in range(10):
+                    for x in range(38):
+                        v = np.float32(0)
+                        for r in range(4):
+                            th = y - r
+                            if 0 <= th < 7:
+                                v += priv[r, c * 7 + th, x]
+                        gh, gw = h0 - 3 + y, w0 - 3 + x
+                        if 0 <= gh < H and 0 <= gw < W:
+                            out[c, gh, gw] += v
+    assert not np.isnan(out).any() and np.array_equal(out, want)
