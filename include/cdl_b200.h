@@ -41,7 +41,11 @@ enum cdl_status {
 
 enum cdl_precision {
   CDL_PREC_FP32 = 0, /* CUDA-core fp32 FMA: same arithmetic class as the reference on CPU  */
-  CDL_PREC_TF32 = 1  /* tcgen05 kind::tf32, operands rounded RNE, fp32 accumulate in TMEM  */
+  CDL_PREC_TF32 = 1  /* tcgen05 kind::tf32, operands rounded RNE, fp32 accumulate in TMEM.
+                      * Covered geometries: the video network (3-D, 7x7x7, s = 2, C = 1, M <= 176, model/net.py:123-143)
+                      * and the 2-D stride-1 networks (7x7, s = 1, C <= 3, M <= 64, padded width % 4 == 0:
+                      * model/net.py:20-36 with args.json / JDD args, GDLNet :572-600); any other geometry gets the
+                      * FP32 kernels - see cdl_plan_precision().                                                      */
 };
 
 /* Geometry of one plan.  Mirrors the constructor kwargs of the reference modules
