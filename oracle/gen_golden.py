@@ -88,9 +88,31 @@ def _dump(name, net, y, sigma, mask, gabor=False, trace=True, extra=None):
           f"|xhat|max={float(xhat.abs().max()):.3f} -> {os.path.getsize(path) / 1024:.0f} KB")
 
 
+def tc2_cases(ref):
+    """Fixtures at geometries the 2-D tensor-core kernels cover (7x7, s = 1, C <= 3, M <= 64, W % 4 == 0), each with its
+    own generator so that adding them leaves the cases below untouched:  python oracle/gen_golden.py tc2"""
+    # 9. JDD like trained_nets/JDD_CDLNet-s0120 (s = 1, C = 3, Bayer mask, per-sample sigma), M = 20 -> GEMM N = 32,
+    #    36 rows = 2.25 analysis tiles, 44 columns = 1.4 tiles
+    g = torch.Generator().manual_seed(91)
+    net = ref.CDLNet(K=4, M=20, P=7, s=1, C=3, t0=0, adaptive=True, init=False)
+    _set_weights(net, 0.03, g)
+    y = torch.rand(2, 3, 36, 44, generator=g)
+    mask = ref._ref_root_utils.gen_bayer_mask(y)
+    _dump("cdlnet2d_jdd_s1_w4", net, mask * y, torch.tensor([8.0, 16.0]).reshape(2, 1, 1, 1), mask, trace=False)
+    # 10. Gabor dictionary, colour, stride 1 (BASELINE config 4's family), order 1, M = 16
+    g = torch.Generator().manual_seed(92)
+    net = ref.GDLNet(K=3, M=16, P=7, s=1, C=3, t0=0, order=1, adaptive=True, init=False)
+    _refshim.fix_gdlnet(net)
+    _set_weights(net, 0.025, g, gabor=True)      # stride 1 keeps 4x the energy of the stride-2 case above: half the amplitude
+    _dump("gdlnet_s1_c3", net, torch.rand(1, 3, 24, 40, generator=g), 15.0, None, gabor=True, trace=False)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ref = _refshim.load()
+    if sys.argv[1:] == ["tc2"]:
+        tc2_cases(ref)
+        sys.exit(0)
     g = torch.Generator().manual_seed(1234)
     R = lambda *sh: torch.rand(*sh, generator=g)
 
@@ -144,3 +166,4 @@ if __name__ == "__main__":
                 rows.append([D, H, W, *pad, *ru.unpad_3d(x, pad).shape[2:]])
     np.savez_compressed(os.path.join(OUT, "unpad3d_table.npz"), table=np.array(rows, dtype=np.int64))
     print("unpad3d_table:", rows)
+    tc2_cases(ref)

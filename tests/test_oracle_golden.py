@@ -17,7 +17,8 @@ import torch
 import cdl_oracle as O
 
 CASES = ["cdlnet2d_s2", "cdlnet2d_jdd_mask", "video_s2_p777", "video_s2_p995_odd",
-         "video_s1_p775_c2", "gdlnet_s2_c3", "cdlnet2d_nonadaptive"]
+         "video_s1_p775_c2", "gdlnet_s2_c3", "cdlnet2d_nonadaptive",
+         "cdlnet2d_jdd_s1_w4", "gdlnet_s1_c3"]        # the last two: geometries of the 2-D tensor-core kernels
 
 
 def load(golden_dir, name):

@@ -146,20 +146,3 @@ def test_forward_parity_vs_oracle_cfg1b_like(mode):
     print(f"tc2 forward (CDL_TC2D={mode}): max|xhat-oracle|={ex:.3e} max|z-oracle|={(z.cpu() - zr).abs().max().item():.3e}")
     assert ex <= 1e-4, ex
 
-
-def test_golden_fixture_2d_stride1_auto():
-    """The reference-generated golden vector of the 2-D stride-1 network (sigma=None, non-adaptive, M = 8 -> GEMM N = 16)
-    through the default (`auto`) family = the tensor-core kernels: max|xhat - reference| <= 1e-4 (north_star's bar)."""
-    import numpy as np
-    from util import case_inputs, load_case, module_from_case
-    d = load_case("cdlnet2d_nonadaptive")
-    net = module_from_case(d, "cdlnet2d_nonadaptive").cuda()
-    net.precision = "auto"
-    y, sigma, mask = case_inputs(d, torch.device("cuda", 0))
-    with torch.no_grad():
-        xhat, z = net(y, sigma, mask=mask)
-    plan = next(iter(net._plans.values()))
-    assert plan.precision == "tf32" and plan.launch_count() > 0
-    ex = np.abs(xhat.cpu().numpy() - d["xhat"]).max()
-    assert tuple(xhat.shape) == d["xhat"].shape and tuple(z.shape) == d["z"].shape
-    assert ex <= 1e-4, ex
