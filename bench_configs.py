@@ -143,6 +143,15 @@ def main():
         plan = next(iter(net._plans.values()))
         vox = world * shape[0] * shape[2] * shape[3]
         flops = 2 * K * 2.0 * (vox / s ** 2) * M * C * P * P
+        # z makes one HBM round trip per iteration; images: preprocess 2 reads, K reads of yp (+ K-1 of the
+        # mask), one write of xhat.  2-D configurations are HBM-bound on tensor cores (AI 24-72 FLOP/B).
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm = 6650.0
+        bytes_fwd = 8.0 * K * (vox / s ** 2) * M + 4.0 * vox * C * (K + 2 + (K - 1 if use_mask else 0))
+        out.update(algorithmic_bytes=bytes_fwd, hbm_floor_ms=bytes_fwd / (hbm * 1e9) * 1e3 / world,
+                   frac_of_hbm_roofline=bytes_fwd / (hbm * 1e9) * 1e3 / world / ms)
         out.update(workload=f"{args.config}: {type(net).__name__}(K={K},M={M},P={P},s={s},C={C}) on {world}x{tuple(shape)}"
                             f"{' + Bayer mask' if use_mask else ''}", precision=plan.precision, scaling="weak",
                    value=vox / (ms * 1e-3) / 1e6, ms_per_step=ms, tflops=flops / (ms * 1e-3) / 1e12)
