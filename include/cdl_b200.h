@@ -103,8 +103,8 @@ int cdl_center_pad(cdl_plan_t* plan, const float* y, const float* mask, const fl
 int cdl_preprocess(cdl_plan_t* plan, const float* y, const float* mask, float* yp, float* mask_p, float* mean, void* workspace, void* stream);
 
 /* The stepwise entry points keep the sparse code in the plan's INTERNAL layout (`code`, cdl_plan_code_bytes bytes):
- * (N,M,coarse) for the fp32 kernels, an opaque blocked channels-last layout (176 padded subbands, rows padded to 8
- * sites) for the tensor-core kernels - treat it as a byte buffer.  Convert with cdl_code_export / cdl_code_import; cdl_forward / cdl_denoise always return z as (N,M,coarse).                      */
+ * (N,M,coarse) for the fp32 kernels and the 2-D tensor-core kernels, an opaque blocked channels-last layout (176 padded
+ * subbands, rows padded to 8 sites) for the video tensor-core kernels - treat it as a byte buffer.  Convert with cdl_code_export / cdl_code_import; cdl_forward / cdl_denoise always return z as (N,M,coarse).                      */
 int cdl_plan_code_bytes(const cdl_plan_t* plan, size_t* out);
 int cdl_code_export(cdl_plan_t* plan, const float* code, float* z, void* stream);
 int cdl_code_import(cdl_plan_t* plan, const float* z, float* code, void* stream);
