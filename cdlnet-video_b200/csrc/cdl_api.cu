@@ -16,6 +16,7 @@
 #include "cdl_tc_analysis.cuh"
 #include "cdl_tc_synthesis.cuh"
 #include "cdl_tc2_analysis.cuh"
+#include "cdl_tc2_analysis_x3.cuh"
 #include "cdl_tc2_synthesis.cuh"
 #include "cdl_tc2_synthesis_v2.cuh"
 
@@ -114,6 +115,7 @@ struct cdl_plan {
   size_t wA2_layer;
   size_t tc2_smem;
   bool tc2_syn;        // residual synthesis on the tensor cores too (cdl_tc2_synthesis.cuh)
+  bool tc2_ana_x3;     // candidate 3-term (hi/lo) analysis (cdl_tc2_analysis_x3.cuh), opt-in with CDL_TC2D_ANA=3; not yet validated on hardware
   bool tc2_syn_v2;     // candidate col2im (cdl_tc2_synthesis_v2.cuh), opt-in with CDL_TC2D_SYN=2; not yet validated on hardware
   bool tc2_maskpass;   // JDD mask applied by an image pass after the scatter-add instead of inside the footprint flush
   float* wB2;          // [K][Ng/8][176*8] tf32 filters in UMMA layout
@@ -310,6 +312,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   if (d->precision == CDL_PREC_TF32 && tc2_geom && tc2_mode != 0) {
     p->tc2_ana = true;
     p->tc2_syn = tc2_mode >= 2;
+    p->tc2_ana_x3 = getenv("CDL_TC2D_ANA") && atoi(getenv("CDL_TC2D_ANA")) == 3;
     p->tc2_syn_v2 = p->tc2_syn && getenv("CDL_TC2D_SYN") && atoi(getenv("CDL_TC2D_SYN")) == 2;
     // JDD mask as one image pass after the scatter-add (default; measured 5.5 vs 10.0 ms per synthesis on config 3) or,
     // with CDL_TC2D_MASKPASS=0, inside the footprint flush
@@ -411,12 +414,14 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     int dev_sms = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device);
     p->sm_count = dev_sms;
-    p->wA2_layer = (size_t)tc2::kP * g.C * p->tc2_Ng * 8;
+    p->wA2_layer = (size_t)tc2::kP * g.C * p->tc2_Ng * 8 * (p->tc2_ana_x3 ? 2 : 1);
     p->wB2_layer = (size_t)(p->tc2_Ng / 8) * tc2::kSN * 8;
     if ((e = cudaMalloc(&p->wA2, p->wA2_layer * g.K * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&p->wB2, p->wB2_layer * g.K * sizeof(float))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::syn_smem_bytes(tc2::kNMax))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis_x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc2::smem_layout_x3(tc2::kMaxC, tc2::kNMax).total)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::syn2_smem_bytes(tc2::kNMax))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -568,7 +573,8 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
       }
     }
     if (p->tc2_ana) {
-      tc2::k_pack_tc2_analysis<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
+      if (p->tc2_ana_x3) tc2::k_pack_tc2_analysis_x3<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
+      else tc2::k_pack_tc2_analysis<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
       CDL_LAUNCH_CHECK(p);
       tc2::k_pack_tc2_synthesis<<<32, 256, 0, st>>>(B[k], p->wB2 + (size_t)k * p->wB2_layer, g.M, g.C, p->tc2_Ng);
       CDL_LAUNCH_CHECK(p);
@@ -708,7 +714,10 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     if (ctas > a.ntiles) ctas = a.ntiles;
     CUtensorMap rmap;
     { int rc = make_tmap2d(&rmap, r, p->g); if (rc) return rc; }
-    tc2::k_tc2_analysis<<<ctas, tc2::kThreads, p->tc2_smem, (cudaStream_t)stream_>>>(a, rmap);
+    if (p->tc2_ana_x3)
+      tc2::k_tc2_analysis_x3<<<ctas, tc2::kThreads, tc2::smem_layout_x3(a.C, a.Ng).total, (cudaStream_t)stream_>>>(a, rmap);
+    else
+      tc2::k_tc2_analysis<<<ctas, tc2::kThreads, p->tc2_smem, (cudaStream_t)stream_>>>(a, rmap);
     CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }

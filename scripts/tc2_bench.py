@@ -50,7 +50,8 @@ def main():
         outs = {}
         # arms: fp32 = exact CUDA-core kernels (CDL_TC2D=0), tc2 = tensor-core analysis + residual synthesis (the default),
         # tc2fm = the same with the JDD mask applied inside the footprint flush (CDL_TC2D_MASKPASS=0),
-        # tc2v2 = the candidate col2im of cdl_tc2_synthesis_v2.cuh (CDL_TC2D_SYN=2)
+        # tc2v2 = the candidate col2im of cdl_tc2_synthesis_v2.cuh (CDL_TC2D_SYN=2),
+        # tc2x3 = the candidate 3-term analysis of cdl_tc2_analysis_x3.cuh (CDL_TC2D_ANA=3)
         arms = os.environ.get("TC2_ARMS", "fp32,tc2").split(",")
         for tag in arms:
             net.__dict__.pop("_plans", None)
@@ -61,6 +62,9 @@ def main():
                 os.environ["CDL_TC2D_MASKPASS"] = "0"
             if tag == "tc2v2":
                 os.environ["CDL_TC2D_SYN"] = "2"
+            os.environ.pop("CDL_TC2D_ANA", None)
+            if tag == "tc2x3":
+                os.environ["CDL_TC2D_ANA"] = "3"
 
             def fwd():
                 with torch.no_grad():
@@ -86,6 +90,7 @@ def main():
         os.environ.pop("CDL_TC2D", None)
         os.environ.pop("CDL_TC2D_MASKPASS", None)
         os.environ.pop("CDL_TC2D_SYN", None)
+        os.environ.pop("CDL_TC2D_ANA", None)
         vox = shape[0] * shape[2] * shape[3]
         for tag in arms:
             res[f"{tag}_Mpix_s"] = vox / (res[f"{tag}_forward_ms"] * 1e-3) / 1e6

@@ -20,7 +20,8 @@ def tf32(x):
     return ((b + 0x1000) & ~0x1fff).view(torch.float32)
 
 
-def forward(d):
+def forward(d, analysis="tf32"):
+    """analysis: "tf32" = the default kernels; "3term" = the hi/lo analysis of cdl_tc2_analysis_x3.cuh (CDL_TC2D_ANA=3)."""
     y = torch.from_numpy(d["y"])
     A = [torch.from_numpy(a) for a in d["A"]]
     B = [torch.from_numpy(b) for b in d["B"]]
@@ -31,7 +32,12 @@ def forward(d):
         sigma = torch.from_numpy(sigma)
     yp, mean, pad, mp = O.pre_process_t(y, 1, mask)
     c = 0 if sigma is None or not d["adaptive"] else sigma / 255.0
-    ana = lambda r, w: F.conv2d(tf32(r), tf32(w), padding=3)
+    def ana(r, w):
+        rh, wh = tf32(r), tf32(w)
+        u = F.conv2d(rh, wh, padding=3)
+        if analysis == "3term":
+            u = u + F.conv2d(tf32(r - rh), wh, padding=3) + F.conv2d(rh, tf32(w - wh), padding=3)
+        return u
     syn = lambda z, w: F.conv_transpose2d(tf32(z), tf32(w), padding=3)
     z = O.soft_threshold_t(ana(yp, A[0]), t[0, :1] + c * t[0, 1:2])
     for k in range(1, len(A)):
@@ -46,4 +52,6 @@ if __name__ == "__main__":
     for name in sys.argv[1:] or ["cdlnet2d_nonadaptive", "cdlnet2d_jdd_s1_w4", "gdlnet_s1_c3"]:
         d = load_case(name)
         xhat, z = forward(d)
-        print(f"{name}: predicted max|xhat - reference| = {np.abs(xhat.numpy() - d['xhat']).max():.3e}   max|z - reference| = {np.abs(z.numpy() - d['z']).max():.3e}")
+        x3, _ = forward(d, analysis="3term")
+        print(f"{name}: predicted max|xhat - reference| = {np.abs(xhat.numpy() - d['xhat']).max():.3e}   max|z - reference| = {np.abs(z.numpy() - d['z']).max():.3e}"
+              f"   with the 3-term analysis: {np.abs(x3.numpy() - d['xhat']).max():.3e}")

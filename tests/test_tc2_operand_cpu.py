@@ -283,3 +283,25 @@ def test_synthesis_v2_private_footprints_equal_conv_transpose2d(C, M, H, W):
                         if 0 <= gh < H and 0 <= gw < W:
                             out[c, gh, gw] += v
     assert not np.isnan(out).any() and np.array_equal(out, want)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# candidate 3-term analysis (cdl_tc2_analysis_x3.cuh): generated from k_tc2_analysis, eight operand copies
+# ------------------------------------------------------------------------------------------------------------
+def test_analysis_x3_is_the_validated_kernel_plus_three_edits():
+    x3 = open(os.path.join(os.path.dirname(HDR), "cdl_tc2_analysis_x3.cuh")).read()
+    body = lambda t, name: t[t.index("__global__ void __launch_bounds__(kThreads, 1) " + name):]
+    a, b = body(SRC, "k_tc2_analysis(").splitlines(), body(x3, "k_tc2_analysis_x3(").splitlines()
+    import difflib
+    changed = [l for l in difflib.unified_diff(a, b, lineterm="", n=0) if l[:1] in "+-" and l[:3] not in ("+++", "---")]
+    assert 10 <= len(changed) <= 40, len(changed)              # a handful of edited lines, everything else identical
+    assert "if (k >= 0 && k < kRW) { o[rho * cp - rho] = v; o[(4 + rho) * cp - rho] = vl; }" in x3
+    assert "adesc0 + (uint64_t)((aoff + 4 * L.copy_pitch) >> 4), bdesc0 + (uint64_t)ks * bstep, idesc, 1);" in x3
+    assert "adesc0 + (uint64_t)(aoff >> 4), bdesc_lo + (uint64_t)ks * bstep, idesc, 1);" in x3
+    # shared memory: two filter banks + ONE buffer of eight copies + two staging buffers
+    C, Ng = 3, 64
+    a128 = lambda v: (v + 127) // 128 * 128
+    total = a128(a128(2 * 7 * C * Ng * 32) + 8 * C * ROWS * RW * 4) + 2 * a128(C * ROWS * SW * 4) + 512 + 128
+    assert total == 86016 + 76032 + 21248 + 640 and total <= 227 * 1024
+    # every descriptor start stays inside the 14-bit (16-byte units) address field
+    assert (86016 + 8 * C * ROWS * RW * 4) // 16 < 2 ** 14

@@ -32,3 +32,13 @@ def test_predicted_parity_on_reference_golden_vectors(name, bound):
     xhat, z = forward(d)
     ex = np.abs(xhat.numpy() - d["xhat"]).max()
     assert ex <= bound <= 1e-4, ex
+
+
+@pytest.mark.parametrize("name", ["cdlnet2d_jdd_s1_w4", "gdlnet_s1_c3", "cdlnet2d_nonadaptive"])
+def test_three_term_analysis_model(name):
+    """The candidate accurate mode (cdl_tc2_analysis_x3.cuh, CDL_TC2D_ANA=3): u = r_hi W_hi + r_lo W_hi + r_hi W_lo.
+    With it the remaining error is the residual synthesis's; it must not be worse than the single-pass analysis."""
+    d = load_case(name)
+    e1 = np.abs(forward(d)[0].numpy() - d["xhat"]).max()
+    e3 = np.abs(forward(d, analysis="3term")[0].numpy() - d["xhat"]).max()
+    assert e3 <= 7e-5 and e3 <= e1 * 1.05, (e1, e3)
