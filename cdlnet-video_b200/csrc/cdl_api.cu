@@ -108,7 +108,7 @@ struct cdl_plan {
   float* wBtc;         // [K][2 ranks][176*176]
   float* wBtc_lo;      // layer 0 only: tf32(W - tf32(W)), for the 3-term final synthesis
   size_t wAtc_layer, wBtc_layer;
-  // experimental tcgen05 analysis for 2D, 7x7, s = 1, C <= 3, M <= 64 (cdl_tc2_analysis.cuh); opt-in with CDL_TC2D=1
+  // tcgen05 family for 2D, 7x7, s = 1, C <= 3, M <= 64 (cdl_tc2_analysis.cuh, cdl_tc2_synthesis.cuh); CDL_TC2D=0 disables
   bool tc2_ana;
   int tc2_Ng;          // GEMM N: M rounded up to 16
   float* wA2;          // [K][7*C][Ng*8] tf32 filters in UMMA layout
@@ -305,7 +305,8 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   const bool tc_geom = nd3 && Pd == 7 && Ph == 7 && Pw == 7 && s == 2 && d->C == 1 && d->M <= tc::kNA && (L.fine[2] % 4) == 0 && (L.fine[1] % 2) == 0 && !d->has_mask;
   if (d->precision == CDL_PREC_TF32 && tc_geom) { p->tc_ana = true; p->tc_syn = (getenv("CDL_TC_SYN") ? atoi(getenv("CDL_TC_SYN")) != 0 : true); p->precision_eff = CDL_PREC_TF32; }
 
-  // experimental 2-D tensor-core analysis (the synthesis stays on the fp32 CUDA-core kernel, same planar code layout)
+  // 2-D tensor-core family: same planar code layout as the fp32 kernels, so the two can be mixed step by step (the final
+  // D z always runs on the fp32 kernel)
   const bool tc2_geom = !nd3 && Ph == 7 && Pw == 7 && s == 1 && d->C <= tc2::kMaxC && d->M <= tc2::kNMax && (L.fine[2] % 4) == 0;
   // CDL_TC2D: 0 = off (fp32 CUDA-core kernels), 1 = tensor-core analysis only, 2 (default) = analysis + residual synthesis
   const int tc2_mode = getenv("CDL_TC2D") ? atoi(getenv("CDL_TC2D")) : 2;
