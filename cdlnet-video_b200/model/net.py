@@ -129,9 +129,55 @@ class _ISTANet(nn.Module):
         """ LISTA + D w/ noise-adaptive thresholds """
         if not self._native_ok(y, sigma, mask):
             return self._forward_stock(y, sigma, mask)
+        if self._embed3d_ok(y, mask):
+            return self._forward_embedded3d(y, sigma)
         plan, y, mask, c = self._prepare(y, sigma, mask)
         with torch.cuda.device(y.device):
             return plan.denoise(y, mask, c)
+
+    # -- opt-in: 2-D stride-2 grayscale nets (CDLNet-s2030, BASELINE config 1) on the VIDEO tensor-core kernels ------
+    # A 2-D image is a clip of two frames (image, zero) and a 7x7 filter is the td = 3 slice of a 7x7x7 filter: with
+    # stride 2 and padding 3 along d the only coarse frame reads fine frames td - 3 = 0 (td = 3) and 1 (td = 4, a zero
+    # slice), and the synthesis writes frame 0 from td = 3 and nothing into frame 1 - the 3-D operator restricted to
+    # frame 0 IS the 2-D operator.  6/7 of the MMAs multiply zeros, but the problem (one 256x256 image) is launch-bound
+    # either way.  NOT yet run on hardware: enabled only by CDL_EMBED3D=1 together with precision "tf32"/"auto".
+    def _embed3d_ok(self, y, mask):
+        if os.environ.get("CDL_EMBED3D", "0") != "1" or self.precision not in ("tf32", "auto"):
+            return False
+        if self._nsp != 2 or type(self).__name__ != "CDLNet" or torch.is_tensor(mask):
+            return False
+        if not (self.s == 2 and self._P3() == (7, 7) and y.shape[1] == 1 and self.M <= 176):
+            return False
+        return (-(-y.shape[3] // 2) * 2) % 4 == 0            # the video kernels need a padded width that is a multiple of 4
+
+    def _forward_embedded3d(self, y, sigma):
+        y = y.contiguous()
+        N, dev = y.shape[0], y.device
+        plans = self.__dict__.setdefault("_plans", {})
+        with torch.cuda.device(dev):
+            k2 = (tuple(y.shape), False, dev.index, "fp32")
+            p2 = plans.get(k2)
+            if p2 is None:                                   # pre/post-processing and the index layout: the 2-D plan
+                p2 = plans[k2] = Plan(2, N, 1, self.M, self.K, tuple(y.shape[2:]), (7, 7), 2, precision="fp32", device=dev.index or 0)
+            k3 = (tuple(y.shape), "embed3d", dev.index, "tf32")
+            p3 = plans.get(k3)
+            if p3 is None:                                   # two frames of the PADDED image: no further stride padding
+                p3 = plans[k3] = Plan(3, N, 1, self.M, self.K, (2, *p2.fine[1:]), (7, 7, 7), 2, precision="tf32", device=dev.index or 0)
+            if p3.precision != "tf32":
+                raise RuntimeError("CDL_EMBED3D=1: the video tensor-core kernels do not cover this geometry")
+            key = self._weights_key()
+            if p3._weights_key != key:
+                def lift(w):                                 # (M,1,7,7) -> (M,1,7,7,7), the filter sits in the td = 3 slice
+                    w3 = torch.zeros(w.shape[0], 1, 7, 7, 7, dtype=torch.float32, device=dev)
+                    w3[:, :, 3] = w.detach().to(dev, torch.float32)
+                    return w3
+                p3.set_weights([lift(m.weight) for m in self.A], [lift(m.weight) for m in self.B], self.t, key=key)
+            yp, _, mean = p2.preprocess(y)
+            yp3 = torch.zeros(N, 1, 2, *yp.shape[2:], dtype=torch.float32, device=dev)
+            yp3[:, :, 0] = yp
+            z3, xp3 = p3.forward(yp3, None, self._c_vector(sigma, N, dev))
+            xhat = p2.postprocess(xp3[:, :, 0].contiguous(), mean)
+            return xhat, z3[:, :, 0]
 
     def forward_generator(self, y, sigma=None, mask=1):
         """ same as forward but yields intermediate sparse codes z_0..z_{K-1}, then xhat """

@@ -11,6 +11,8 @@ L=gpurun_out/tc2_bringup.log
   CDL_RUN_EXPERIMENTAL=1 timeout -s KILL ${1:-150} python -m pytest tests/test_tc2_gpu.py -q -s -k "x3" 2>&1 | tail -40
   echo "== candidate: write-once col2im (CDL_TC2D_SYN=2)"
   CDL_RUN_EXPERIMENTAL=1 timeout -s KILL ${1:-150} python -m pytest tests/test_tc2_gpu.py -q -s -k "v2" 2>&1 | tail -40
+  echo "== candidate: config 1 on the video kernels (CDL_EMBED3D=1)"
+  CDL_RUN_EXPERIMENTAL=1 timeout -s KILL ${1:-150} python -m pytest tests/test_zz_embed3d_gpu.py -q -s 2>&1 | tail -20
 } > $L 2>&1
 cat $L
 timeout -s KILL 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
