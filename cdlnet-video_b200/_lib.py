@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libcdl_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ldl"]
 
 SYMBOLS = [
     "cdl_abi_version", "cdl_status_string", "cdl_plan_create", "cdl_plan_destroy", "cdl_plan_layout",
@@ -23,6 +23,9 @@ SYMBOLS = [
     "cdl_mean_from_sums", "cdl_center_pad", "cdl_preprocess", "cdl_analysis_step", "cdl_synthesis_step",
     "cdl_forward", "cdl_postprocess", "cdl_denoise", "cdl_plan_host_workspace_bytes", "cdl_denoise_host",
     "cdl_plan_launch_count", "cdl_plan_code_bytes", "cdl_code_export", "cdl_code_import", "cdl_plan_set_rearm",
+    "cdl_plan_reduce_workspace_bytes", "cdl_plan_step_workspace_bytes", "cdl_plan_host_workspace_bytes_noz",
+    "cdl_comm_unique_id", "cdl_comm_create", "cdl_comm_destroy", "cdl_comm_allreduce_f64", "cdl_halo_bytes",
+    "cdl_halo_exchange", "cdl_analysis_step_halo", "cdl_halo_add", "cdl_forward_sharded",
 ]
 
 
@@ -97,7 +100,8 @@ def load():
         lib.cdl_plan_destroy.argtypes = [vp]
         lib.cdl_plan_layout.restype = i32
         lib.cdl_plan_layout.argtypes = [vp, P(CdlLayout)]
-        for name in ("cdl_plan_workspace_bytes", "cdl_plan_host_workspace_bytes", "cdl_plan_code_bytes"):
+        for name in ("cdl_plan_workspace_bytes", "cdl_plan_host_workspace_bytes", "cdl_plan_code_bytes",
+                     "cdl_plan_reduce_workspace_bytes", "cdl_plan_step_workspace_bytes", "cdl_plan_host_workspace_bytes_noz"):
             getattr(lib, name).restype = i32
             getattr(lib, name).argtypes = [vp, P(ctypes.c_size_t)]
         lib.cdl_plan_precision.restype = i32
@@ -131,6 +135,24 @@ def load():
         lib.cdl_denoise.argtypes = [vp] * 8
         lib.cdl_denoise_host.restype = i32
         lib.cdl_denoise_host.argtypes = [vp] * 8
+        lib.cdl_comm_unique_id.restype = i32
+        lib.cdl_comm_unique_id.argtypes = [vp]
+        lib.cdl_comm_create.restype = i32
+        lib.cdl_comm_create.argtypes = [P(vp), vp, i32, i32, i32]
+        lib.cdl_comm_destroy.restype = None
+        lib.cdl_comm_destroy.argtypes = [vp]
+        lib.cdl_comm_allreduce_f64.restype = i32
+        lib.cdl_comm_allreduce_f64.argtypes = [vp, vp, ctypes.c_size_t, vp]
+        lib.cdl_halo_bytes.restype = i32
+        lib.cdl_halo_bytes.argtypes = [vp, P(ctypes.c_size_t)]
+        lib.cdl_halo_exchange.restype = i32
+        lib.cdl_halo_exchange.argtypes = [vp] * 6
+        lib.cdl_analysis_step_halo.restype = i32
+        lib.cdl_analysis_step_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.cdl_halo_add.restype = i32
+        lib.cdl_halo_add.argtypes = [vp] * 6
+        lib.cdl_forward_sharded.restype = i32
+        lib.cdl_forward_sharded.argtypes = [vp] * 9
         if lib.cdl_abi_version() != 1:
             raise RuntimeError("libcdl_b200.so ABI version mismatch")
         _lib = lib

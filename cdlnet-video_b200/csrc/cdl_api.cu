@@ -5,6 +5,7 @@
 // Every arithmetic step runs in a hand-written sm_100a kernel; there is no CPU or library fallback.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 #include <new>
@@ -27,8 +28,12 @@ namespace {
 typedef void (*ana_fn_t)(const AnaParams);
 typedef void (*syn_fn_t)(const SynParams);
 
-struct Offsets {   // byte offsets into the caller's workspace
-  size_t rbuf, partial, sums, yp, mask_p, mean, xphat, code, rtf32, rtf32s, end;
+// Byte offsets into the caller's workspace.  The regions are ordered so that every smaller use is a PREFIX of the
+// larger one: [reduce: partial sums, sums, mean] [step: tf32 copies of r] [forward: r, yp, mask_p, xphat, code]
+// [host staging].  A driver that only reduces sums, or only calls the stepwise entry points, allocates the prefix
+// (cdl_plan_reduce_workspace_bytes / cdl_plan_step_workspace_bytes).
+struct Offsets {
+  size_t partial, sums, mean, reduce_end, rtf32, rtf32s, step_end, rbuf, yp, mask_p, xphat, code, end;
   size_t h_y, h_mask, h_c, h_xhat, h_z, h_end;
 };
 
@@ -134,7 +139,27 @@ struct cdl_plan {
   size_t code_bytes;   // bytes of the sparse code in the plan's internal layout
   Offsets off;
   uint64_t launches;
+  int dbg_mode;        // CDL_TC_DBG_MODE, read once at plan creation (development aid)
+  // tensor maps are encoded once per (base pointer, pitch): the stepwise drivers and cdl_forward present the same few
+  // buffers on every iteration
+  struct MapSlot { const void* base; int width; CUtensorMap map; };
+  MapSlot maps[4];
+  int map_next;
 };
+
+// cached tensor map of a buffer (encode on first sight, round-robin replacement)
+template <typename MakeFn>
+static int cached_tmap(cdl_plan* p, const float* base, int width, MakeFn make, const CUtensorMap** out) {
+  for (int i = 0; i < 4; ++i)
+    if (p->maps[i].base == base && p->maps[i].width == width) { *out = &p->maps[i].map; return CDL_OK; }
+  cdl_plan::MapSlot& sl = p->maps[p->map_next];
+  int rc = make(&sl.map);
+  if (rc) { sl.base = nullptr; return rc; }
+  sl.base = base; sl.width = width;
+  p->map_next = (p->map_next + 1) & 3;
+  *out = &sl.map;
+  return CDL_OK;
+}
 
 #define CDL_CUDA(call)                                   \
   do {                                                   \
@@ -242,6 +267,8 @@ extern "C" const char* cdl_status_string(int s) {
     case CDL_ERR_RANGE: return "index out of range";
     case CDL_ERR_WORKSPACE: return "workspace missing or too small";
   }
+  if (s == CDL_ERR_NO_NCCL) return "libnccl.so.2 could not be loaded";
+  if (s >= CDL_NCCL_ERROR_BASE) return "NCCL error (ncclResult_t = status - 2000)";
   if (s >= CDL_CUDA_ERROR_BASE) return cudaGetErrorString((cudaError_t)(s - CDL_CUDA_ERROR_BASE));
   return "unknown status";
 }
@@ -265,6 +292,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   if (!p) return CDL_CUDA_ERROR_BASE + (int)cudaErrorMemoryAllocation;
   memset(p, 0, sizeof(*p));
   p->desc = *d;
+  p->dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
   const int s = d->s;
   const bool slab = d->halo_front || d->halo_back;
 
@@ -445,16 +473,18 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     const size_t in_bytes = (size_t)g.N * g.C * D * H * W * sizeof(float);
     const size_t z_bytes = (size_t)g.N * g.M * g.coarse_vol() * sizeof(float);
     size_t cur = 0;
-    o.rbuf = cur; cur = align_up(cur + fine_bytes, 256);
     o.partial = cur; cur = align_up(cur + (size_t)g.N * 2 * kRedBlocksPerSample * sizeof(double), 256);
     o.sums = cur; cur = align_up(cur + (size_t)g.N * 2 * sizeof(double), 256);
-    o.yp = cur; cur = align_up(cur + fine_bytes, 256);
-    o.mask_p = cur; cur = align_up(cur + (d->has_mask ? fine_bytes : 0), 256);
     o.mean = cur; cur = align_up(cur + (size_t)g.N * sizeof(float), 256);
-    o.xphat = cur; cur = align_up(cur + fine_bytes, 256);
-    o.code = cur; cur = align_up(cur + p->code_bytes, 256);
+    o.reduce_end = cur;
     o.rtf32 = cur; cur = align_up(cur + (p->tc_ana ? fine_bytes : 0), 256);                     // tf32(r)
     o.rtf32s = cur; cur = align_up(cur + (p->tc_ana ? fine_bytes / L.fine[2] * (L.fine[2] + 4) : 0), 256);   // tf32(r), rows shifted by 2 floats
+    o.step_end = cur;
+    o.rbuf = cur; cur = align_up(cur + fine_bytes, 256);
+    o.yp = cur; cur = align_up(cur + fine_bytes, 256);
+    o.mask_p = cur; cur = align_up(cur + (d->has_mask ? fine_bytes : 0), 256);
+    o.xphat = cur; cur = align_up(cur + fine_bytes, 256);
+    o.code = cur; cur = align_up(cur + p->code_bytes, 256);
     o.end = cur;
     o.h_y = cur; cur = align_up(cur + in_bytes, 256);
     o.h_mask = cur; cur = align_up(cur + (d->has_mask ? in_bytes : 0), 256);
@@ -490,9 +520,25 @@ extern "C" int cdl_plan_workspace_bytes(const cdl_plan_t* p, size_t* out) {
   *out = p->off.end;
   return CDL_OK;
 }
+extern "C" int cdl_plan_step_workspace_bytes(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->off.step_end > 256 ? p->off.step_end : 256;
+  return CDL_OK;
+}
+extern "C" int cdl_plan_reduce_workspace_bytes(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->off.reduce_end;
+  return CDL_OK;
+}
 extern "C" int cdl_plan_host_workspace_bytes(const cdl_plan_t* p, size_t* out) {
   if (!p || !out) return CDL_ERR_NULL;
   *out = p->off.h_end;
+  return CDL_OK;
+}
+// the staging area of z is the last region: callers that pass z_host == NULL need only this prefix
+extern "C" int cdl_plan_host_workspace_bytes_noz(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = p->off.h_z;
   return CDL_OK;
 }
 extern "C" int cdl_plan_precision(const cdl_plan_t* p) { return p ? p->precision_eff : CDL_ERR_NULL; }
@@ -657,7 +703,16 @@ extern "C" int cdl_postprocess(cdl_plan_t* p, const float* xphat, const float* m
 // ------------------------------------------------------------------------------------------------
 // ISTA steps
 // ------------------------------------------------------------------------------------------------
-extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, void* ws, void* stream_) {
+static int halo_add_launch(cdl_plan* p, float* r, const tc::HaloFuse& h, cudaStream_t st) {
+  const long long total = 2LL * h.ov * h.frame4 * p->g.N;
+  long long blocks = (total + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  tc::k_halo_add<<<(int)blocks, 256, 0, st>>>(r, h, p->g.N);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
+}
+
+static int analysis_step_impl(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, void* ws, void* stream_,
+                              const tc::HaloFuse* halo) {
   if (!p || !r || !z) return CDL_ERR_NULL;
   if (!p->have_weights) return CDL_ERR_NO_WEIGHTS;
   if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
@@ -675,7 +730,7 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     a.tiles_h = ceil_div(p->g.Qh, tc::kATile);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
     a.dbg = g_tc_dbg;
-    a.dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
+    a.dbg_mode = p->dbg_mode;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
     if (!ws) return CDL_ERR_WORKSPACE;
@@ -685,19 +740,24 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
       const long long n4 = (long long)p->g.N * p->g.fine_vol() / 4;
       long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
       const bool arm = (p->rearm_opt || p->rearm_fwd) && p->tc_syn && !first && p->last_yp && r == p->last_out;   // r is dead once read here
-      tc::k_round_tf32<<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4, arm ? p->last_yp : nullptr,
-                                                                       arm ? const_cast<float*>(r) : nullptr);
+      if (halo)
+        tc::k_round_tf32<true><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4, arm ? p->last_yp : nullptr,
+                                                                               arm ? const_cast<float*>(r) : nullptr, *halo);
+      else
+        tc::k_round_tf32<false><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>(r, rr, rs, p->g.Fw / 4, n4, arm ? p->last_yp : nullptr,
+                                                                                arm ? const_cast<float*>(r) : nullptr, tc::HaloFuse{});
       p->armed_buf = arm ? r : nullptr;
       p->armed_yp = arm ? p->last_yp : nullptr;
       CDL_LAUNCH_CHECK(p);
     }
-    CUtensorMap rmap0, rmap1;
-    { int rc = make_fine_tmap(&rmap0, rr, p->g, p->g.Fw); if (rc) return rc; }
-    { int rc = make_fine_tmap(&rmap1, rs, p->g, p->g.Fw + 4); if (rc) return rc; }
-    tc::k_tc_analysis<<<2 * pairs, tc::kAThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a, rmap0, rmap1);
+    const CUtensorMap *rmap0, *rmap1;
+    { int rc = cached_tmap(p, rr, p->g.Fw, [&](CUtensorMap* m) { return make_fine_tmap(m, rr, p->g, p->g.Fw); }, &rmap0); if (rc) return rc; }
+    { int rc = cached_tmap(p, rs, p->g.Fw + 4, [&](CUtensorMap* m) { return make_fine_tmap(m, rs, p->g, p->g.Fw + 4); }, &rmap1); if (rc) return rc; }
+    tc::k_tc_analysis<<<2 * pairs, tc::kAThreads, tc::kAnaSmemBytes, (cudaStream_t)stream_>>>(a, *rmap0, *rmap1);
     CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }
+  if (halo) { int rc = halo_add_launch(p, const_cast<float*>(r), *halo, (cudaStream_t)stream_); if (rc) return rc; }   // no rounding pass to fuse into
   if (p->tc2_ana) {
     tc2::Ana2Params a;
     a.N = p->g.N; a.C = p->g.C; a.M = p->g.M; a.H = p->g.Fh; a.W = p->g.Fw;
@@ -713,12 +773,12 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
     a.ntiles = p->g.N * a.tiles_h * a.tiles_w;
     int ctas = p->sm_count;
     if (ctas > a.ntiles) ctas = a.ntiles;
-    CUtensorMap rmap;
-    { int rc = make_tmap2d(&rmap, r, p->g); if (rc) return rc; }
+    const CUtensorMap* rmap;
+    { int rc = cached_tmap(p, r, p->g.Fw, [&](CUtensorMap* m) { return make_tmap2d(m, r, p->g); }, &rmap); if (rc) return rc; }
     if (p->tc2_ana_x3)
-      tc2::k_tc2_analysis_x3<<<ctas, tc2::kThreads, tc2::smem_layout_x3(a.C, a.Ng).total, (cudaStream_t)stream_>>>(a, rmap);
+      tc2::k_tc2_analysis_x3<<<ctas, tc2::kThreads, tc2::smem_layout_x3(a.C, a.Ng).total, (cudaStream_t)stream_>>>(a, *rmap);
     else
-      tc2::k_tc2_analysis<<<ctas, tc2::kThreads, p->tc2_smem, (cudaStream_t)stream_>>>(a, rmap);
+      tc2::k_tc2_analysis<<<ctas, tc2::kThreads, p->tc2_smem, (cudaStream_t)stream_>>>(a, *rmap);
     CDL_LAUNCH_CHECK(p);
     return CDL_OK;
   }
@@ -735,6 +795,38 @@ extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r
   p->ana_fn<<<grid, kAnaThreads, p->ana_smem, (cudaStream_t)stream_>>>(a);
   CDL_LAUNCH_CHECK(p);
   return CDL_OK;
+}
+
+extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, void* ws, void* stream_) {
+  return analysis_step_impl(p, k, first, r, c, z, ws, stream_, nullptr);
+}
+
+// seam geometry of a slab plan: ov = Pd - s frames shared with each neighbour
+static bool make_halo(const cdl_plan* p, const float* recv_prev, const float* recv_next, const float* yp, tc::HaloFuse* h) {
+  h->prev = p->desc.halo_front ? recv_prev : nullptr;
+  h->next = p->desc.halo_back ? recv_next : nullptr;
+  h->yp = yp;
+  h->ov = p->g.Pd - p->g.sd;
+  h->Fd = p->g.Fd;
+  h->frame4 = (long long)p->g.C * p->g.Fh * p->g.Fw / 4;     // slabs are single-channel today; C folded into the frame for safety
+  return h->prev || h->next;
+}
+
+extern "C" int cdl_analysis_step_halo(cdl_plan_t* p, int k, const float* r, const float* c, float* z, const float* recv_prev,
+                                      const float* recv_next, const float* yp, void* ws, void* stream_) {
+  if (!p) return CDL_ERR_NULL;
+  if (p->g.C != 1 || (p->g.Fh * p->g.Fw) % 4) return CDL_ERR_UNSUPPORTED;
+  tc::HaloFuse h;
+  const bool any = make_halo(p, recv_prev, recv_next, yp, &h);
+  return analysis_step_impl(p, k, 0, r, c, z, ws, stream_, any ? &h : nullptr);
+}
+
+extern "C" int cdl_halo_add(cdl_plan_t* p, float* r, const float* recv_prev, const float* recv_next, const float* yp, void* stream_) {
+  if (!p || !r) return CDL_ERR_NULL;
+  if (p->g.C != 1 || (p->g.Fh * p->g.Fw) % 4) return CDL_ERR_UNSUPPORTED;
+  tc::HaloFuse h;
+  if (!make_halo(p, recv_prev, recv_next, yp, &h)) return CDL_OK;
+  return halo_add_launch(p, r, h, (cudaStream_t)stream_);
 }
 
 extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const float* z, const float* yp, const float* mask_p, float* out, void* ws, void* stream_) {
@@ -769,7 +861,7 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
     a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
     a.dbg = g_tc_dbg;
-    a.dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
+    a.dbg_mode = p->dbg_mode;
     a.a_lo = 0;
     int pairs = p->sm_count / 2;
     if (pairs > a.ntiles) pairs = a.ntiles;
@@ -847,11 +939,12 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
 }
 
 extern "C" int cdl_forward(cdl_plan_t* p, const float* yp, const float* mask_p, const float* c, float* z, float* xphat, void* ws, void* stream_) {
-  if (!p || !yp || !z || !xphat) return CDL_ERR_NULL;
+  if (!p || !yp || !xphat) return CDL_ERR_NULL;
   if (!ws) return CDL_ERR_WORKSPACE;
   float* rbuf = reinterpret_cast<float*>((char*)ws + p->off.rbuf);
-  // the tensor-core kernels keep the code channels-last in the workspace; the fp32 kernels work in place on z
-  float* code = p->tc_ana ? reinterpret_cast<float*>((char*)ws + p->off.code) : z;
+  // the video tensor-core kernels keep the code in their own layout in the workspace; the other kernels work in place on z
+  // (z == NULL: the caller does not want the code back - it stays in the workspace and the export pass is skipped)
+  float* code = (p->tc_ana || !z) ? reinterpret_cast<float*>((char*)ws + p->off.code) : z;
   int rc = cdl_analysis_step(p, 0, 1, yp, c, code, ws, stream_);                   // model/net.py:85,200
   p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
   for (int k = 1; k < p->g.K && !rc; ++k) {                                        // model/net.py:86-87,204-205
@@ -861,12 +954,167 @@ extern "C" int cdl_forward(cdl_plan_t* p, const float* yp, const float* mask_p, 
   }
   p->rearm_fwd = false; p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
   if (!rc) rc = cdl_synthesis_step(p, 0, 0, code, nullptr, nullptr, xphat, ws, stream_);   // D = B[0], model/net.py:90,210
-  if (!rc) rc = cdl_code_export(p, code, z, stream_);
+  if (!rc && z) rc = cdl_code_export(p, code, z, stream_);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// temporal slabs across GPUs: neighbour exchange over NCCL P2P (BASELINE config 5)
+// ------------------------------------------------------------------------------------------------
+// NCCL is resolved at run time from the process (PyTorch's bundled libnccl.so.2 is already loaded in a torchrun rank)
+// so that libcdl_b200.so itself has no link-time dependency on it.
+namespace {
+typedef struct ncclComm* nccl_comm_t;
+struct nccl_uid_t { char internal[128]; };
+struct NcclApi {
+  void* handle;
+  int (*GetUniqueId)(nccl_uid_t*);
+  int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int);
+  int (*CommDestroy)(nccl_comm_t);
+  int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+  int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+};
+NcclApi g_nccl = {};
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0;
+
+int load_nccl() {
+  if (g_nccl.handle) return CDL_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return CDL_ERR_NO_NCCL;
+  NcclApi a = {};
+  a.handle = h;
+#define CDL_SYM(field, name) *(void**)(&a.field) = dlsym(h, name); if (!a.field) return CDL_ERR_NO_NCCL;
+  CDL_SYM(GetUniqueId, "ncclGetUniqueId") CDL_SYM(CommInitRank, "ncclCommInitRank") CDL_SYM(CommDestroy, "ncclCommDestroy")
+  CDL_SYM(Send, "ncclSend") CDL_SYM(Recv, "ncclRecv") CDL_SYM(AllReduce, "ncclAllReduce")
+  CDL_SYM(GroupStart, "ncclGroupStart") CDL_SYM(GroupEnd, "ncclGroupEnd")
+#undef CDL_SYM
+  g_nccl = a;
+  return CDL_OK;
+}
+}  // namespace
+
+struct cdl_comm {
+  nccl_comm_t comm;
+  int rank, nranks, device;
+};
+
+#define CDL_NCCL(call)                                                 \
+  do {                                                                 \
+    int r__ = (call);                                                  \
+    if (r__ != 0) return CDL_NCCL_ERROR_BASE + r__;                    \
+  } while (0)
+
+extern "C" int cdl_comm_unique_id(void* id128) {
+  if (!id128) return CDL_ERR_NULL;
+  { int rc = load_nccl(); if (rc) return rc; }
+  nccl_uid_t id;
+  CDL_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return CDL_OK;
+}
+
+extern "C" int cdl_comm_create(cdl_comm_t** out, const void* id128, int rank, int nranks, int device) {
+  if (!out || !id128) return CDL_ERR_NULL;
+  *out = nullptr;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return CDL_ERR_RANGE;
+  { int rc = load_nccl(); if (rc) return rc; }
+  CDL_CUDA(cudaSetDevice(device));
+  nccl_uid_t id;
+  memcpy(&id, id128, sizeof(id));
+  cdl_comm* c = new (std::nothrow) cdl_comm();
+  if (!c) return CDL_CUDA_ERROR_BASE + (int)cudaErrorMemoryAllocation;
+  c->rank = rank; c->nranks = nranks; c->device = device; c->comm = nullptr;
+  int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+  if (r != 0) { delete c; return CDL_NCCL_ERROR_BASE + r; }
+  *out = c;
+  return CDL_OK;
+}
+
+extern "C" void cdl_comm_destroy(cdl_comm_t* c) {
+  if (!c) return;
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  delete c;
+}
+
+extern "C" int cdl_comm_allreduce_f64(cdl_comm_t* c, double* buf, size_t n, void* stream_) {
+  if (!c || !buf) return CDL_ERR_NULL;
+  CDL_NCCL(g_nccl.AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, c->comm, (cudaStream_t)stream_));
+  return CDL_OK;
+}
+
+extern "C" int cdl_halo_bytes(const cdl_plan_t* p, size_t* out) {
+  if (!p || !out) return CDL_ERR_NULL;
+  *out = (size_t)p->g.N * p->g.C * (p->g.Pd - p->g.sd) * p->g.Fh * p->g.Fw * sizeof(float);
+  return CDL_OK;
+}
+
+// One bidirectional exchange of the seam frames of `r` with both neighbours, grouped: my first / last
+// ov = Pd - s resident frames go to rank - 1 / rank + 1, theirs arrive in recv_prev / recv_next ((N, ov, Fh, Fw) each).
+extern "C" int cdl_halo_exchange(cdl_plan_t* p, cdl_comm_t* c, const float* r, float* recv_prev, float* recv_next, void* stream_) {
+  if (!p || !r) return CDL_ERR_NULL;
+  const bool hp = p->desc.halo_front > 0, hn = p->desc.halo_back > 0;
+  if (!hp && !hn) return CDL_OK;
+  if (!c) return CDL_ERR_NULL;
+  if ((hp && (!recv_prev || c->rank == 0)) || (hn && (!recv_next || c->rank + 1 >= c->nranks))) return CDL_ERR_RANGE;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const Geo& g = p->g;
+  const size_t frame = (size_t)g.C * g.Fh * g.Fw, ov = (size_t)(g.Pd - g.sd);
+  const size_t seam = ov * frame, sample = (size_t)g.Fd * frame;
+  CDL_NCCL(g_nccl.GroupStart());
+  for (int n = 0; n < g.N; ++n) {                     // the seam frames of one sample are contiguous
+    const float* base = r + (size_t)n * sample;
+    if (hp) {
+      CDL_NCCL(g_nccl.Send(base, seam, kNcclFloat32, c->rank - 1, c->comm, st));
+      CDL_NCCL(g_nccl.Recv(recv_prev + (size_t)n * seam, seam, kNcclFloat32, c->rank - 1, c->comm, st));
+    }
+    if (hn) {
+      CDL_NCCL(g_nccl.Send(base + sample - seam, seam, kNcclFloat32, c->rank + 1, c->comm, st));
+      CDL_NCCL(g_nccl.Recv(recv_next + (size_t)n * seam, seam, kNcclFloat32, c->rank + 1, c->comm, st));
+    }
+  }
+  CDL_NCCL(g_nccl.GroupEnd());
+  return CDL_OK;
+}
+
+// The K iterations + D z of ONE rank's temporal slab (model/net.py:192-212 applied to a clip split along time):
+//   code <- ST(A_0 yp) ; K-1 x [ r <- B_k code - yp (local partial) ; exchange seams ; code <- ST(code - A_k (r + seams)) ] ;
+//   r <- B_0 code ; exchange seams ; r += seams
+// `r` (N,C,Fd,Fh,Fw) ends up holding xphat on the resident frames; halo_ws = 2 x cdl_halo_bytes.  comm may be NULL for
+// a plan without halos (one rank: the same code path without the exchange - the N = 1 point of a strong-scaling run).
+extern "C" int cdl_forward_sharded(cdl_plan_t* p, cdl_comm_t* c, const float* yp, const float* cvec, float* code, float* r,
+                                   void* halo_ws, void* ws, void* stream_) {
+  if (!p || !yp || !code || !r) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  const bool hp = p->desc.halo_front > 0, hn = p->desc.halo_back > 0;
+  if ((hp || hn) && (!c || !halo_ws)) return CDL_ERR_NULL;
+  size_t hb = 0;
+  cdl_halo_bytes(p, &hb);
+  float* recv_prev = reinterpret_cast<float*>(halo_ws);
+  float* recv_next = reinterpret_cast<float*>((char*)halo_ws + hb);
+  const bool saved_rearm = p->rearm_opt;
+  p->rearm_opt = true;                                 // r is this driver's own buffer: let the rounding pass re-arm it with -yp
+  p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
+  int rc = cdl_analysis_step(p, 0, 1, yp, cvec, code, ws, stream_);
+  for (int k = 1; k < p->g.K && !rc; ++k) {
+    rc = cdl_synthesis_step(p, k, 1, code, yp, nullptr, r, ws, stream_);
+    if (!rc) rc = cdl_halo_exchange(p, c, r, recv_prev, recv_next, stream_);
+    p->rearm_opt = k + 1 < p->g.K;                     // another residual synthesis follows
+    if (!rc) rc = cdl_analysis_step_halo(p, k, r, cvec, code, recv_prev, recv_next, yp, ws, stream_);
+  }
+  p->rearm_opt = saved_rearm;
+  p->armed_buf = nullptr; p->last_out = nullptr; p->last_yp = nullptr;
+  if (!rc) rc = cdl_synthesis_step(p, 0, 0, code, nullptr, nullptr, r, ws, stream_);
+  if (!rc) rc = cdl_halo_exchange(p, c, r, recv_prev, recv_next, stream_);
+  if (!rc) rc = cdl_halo_add(p, r, recv_prev, recv_next, nullptr, stream_);
   return rc;
 }
 
 extern "C" int cdl_denoise(cdl_plan_t* p, const float* y, const float* mask, const float* c, float* xhat, float* z, void* ws, void* stream_) {
-  if (!p || !y || !xhat || !z) return CDL_ERR_NULL;
+  if (!p || !y || !xhat) return CDL_ERR_NULL;
   if (!ws) return CDL_ERR_WORKSPACE;
   char* w = (char*)ws;
   float* yp = reinterpret_cast<float*>(w + p->off.yp);
@@ -894,7 +1142,7 @@ extern "C" int cdl_denoise_host(cdl_plan_t* p, const float* y_host, const float*
   float* mask = p->desc.has_mask ? reinterpret_cast<float*>(w + p->off.h_mask) : nullptr;
   float* c = c_host ? reinterpret_cast<float*>(w + p->off.h_c) : nullptr;
   float* xhat = reinterpret_cast<float*>(w + p->off.h_xhat);
-  float* z = reinterpret_cast<float*>(w + p->off.h_z);
+  float* z = z_host ? reinterpret_cast<float*>(w + p->off.h_z) : nullptr;
   CDL_CUDA(cudaMemcpyAsync(y, y_host, in_bytes, cudaMemcpyHostToDevice, st));
   if (mask) CDL_CUDA(cudaMemcpyAsync(mask, mask_host, in_bytes, cudaMemcpyHostToDevice, st));
   if (c) CDL_CUDA(cudaMemcpyAsync(c, c_host, (size_t)g.N * sizeof(float), cudaMemcpyHostToDevice, st));

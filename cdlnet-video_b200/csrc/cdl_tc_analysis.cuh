@@ -103,10 +103,38 @@ __global__ void k_pack_tc_analysis(const float* __restrict__ w, float* __restric
 // Image-sized streams (4 MB per 16x256x256 clip), negligible next to the code traffic.
 // Inside cdl_forward the pass also re-arms the residual buffer for the next synthesis (reset[i] = -yp[i]; reset aliases
 // src, which is dead once read) - one launch and one image pass less per iteration than a separate k_neg_copy.
+// Temporal slabs (cdl_analysis_step_halo): on the Pd - s seam frames a rank shares with a neighbour both hold PARTIAL
+// sums of B z; the neighbour's partial (received into prev / next, (N, ov, Fh, Fw) each) is added here, in the pass that
+// reads r anyway.  In residual mode both partials carry -yp, so yp is added back once.
+struct HaloFuse {
+  const float* prev;      // partial sums of the previous rank on my first `ov` frames (or nullptr)
+  const float* next;      // partial sums of the next rank on my last `ov` frames (or nullptr)
+  const float* yp;        // non-null: add yp back on the seam frames (residual mode)
+  int ov, Fd;
+  long long frame4;       // float4s per frame: Fh * Fw / 4
+};
+
+template <bool HALO>
 __global__ void __launch_bounds__(256) k_round_tf32(const float* src, float* __restrict__ dst0, float* __restrict__ dst1,
-                                                    int Fw4, long long n4, const float* __restrict__ yp, float* reset) {
+                                                    int Fw4, long long n4, const float* __restrict__ yp, float* reset, const HaloFuse h) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(src)[i];
+    if (HALO) {
+      const long long fr = i / h.frame4, within = i - fr * h.frame4;
+      const int f = (int)(fr % h.Fd);
+      const long long n = fr / h.Fd;
+      const float* add = nullptr;
+      if (h.prev && f < h.ov) add = h.prev + ((n * h.ov + f) * h.frame4 + within) * 4;
+      else if (h.next && f >= h.Fd - h.ov) add = h.next + ((n * h.ov + (f - (h.Fd - h.ov))) * h.frame4 + within) * 4;
+      if (add) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(add));
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        if (h.yp) {
+          const float4 y = __ldg(reinterpret_cast<const float4*>(h.yp) + i);
+          v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+        }
+      }
+    }
     if (reset) {
       const float4 y = __ldg(reinterpret_cast<const float4*>(yp) + i);
       reinterpret_cast<float4*>(reset)[i] = make_float4(-y.x, -y.y, -y.z, -y.w);
@@ -121,6 +149,30 @@ __global__ void __launch_bounds__(256) k_round_tf32(const float* src, float* __r
     *reinterpret_cast<float2*>(d + 2) = make_float2(v.x, v.y);
     *reinterpret_cast<float2*>(d + 4) = make_float2(v.z, v.w);
     if (j == Fw4 - 1) *reinterpret_cast<float2*>(d + 6) = make_float2(0.0f, 0.0f);
+  }
+}
+
+// r[seam frames] += neighbour's partial (+ yp): the stand-alone form of the fusion above, for the final D z and for
+// the kernel families whose analysis step has no rounding pass.  One thread per float4 of the 2 * ov seam frames.
+__global__ void __launch_bounds__(256) k_halo_add(float* __restrict__ r, const HaloFuse h, int N) {
+  const long long per = (long long)h.ov * h.frame4;                  // float4s per sample and seam
+  const long long total = 2 * per * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int side = (int)(i / (per * N));                            // 0: head seam (prev), 1: tail seam (next)
+    const long long j = i - (long long)side * per * N;
+    const float* src = side ? h.next : h.prev;
+    if (!src) continue;
+    const long long n = j / per, w = j - n * per;                     // w = frame-in-seam * frame4 + within
+    const long long f0 = side ? (long long)(h.Fd - h.ov) : 0;
+    const long long idx = (n * h.Fd + f0) * h.frame4 + w;
+    float4 v = reinterpret_cast<float4*>(r)[idx];
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + j);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    if (h.yp) {
+      const float4 y = __ldg(reinterpret_cast<const float4*>(h.yp) + idx);
+      v.x += y.x; v.y += y.y; v.z += y.z; v.w += y.w;
+    }
+    reinterpret_cast<float4*>(r)[idx] = v;
   }
 }
 

@@ -5,6 +5,8 @@
 //   run  : ./tc_selftest <cg:1|2> <ts:0|1> <N> <KS>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../cdl_tc_ptx.cuh"
@@ -149,10 +151,22 @@ int main(int argc, char** argv) {
         A[(size_t)m * K + k] = S[(size_t)rk * KS * 1024 + j * 1024 + (ml / 8) * 36 + 4 * (ml % 8) + kk];
       }
   }
-  if (probe) for (auto& v : A) v = 1.0f + 0.75f / 2048.0f;      // 1 + 0.75 ulp_tf32/2...: RNE -> 1 + 2^-10, truncation -> 1
-  if (probe) for (auto& v : B) v = 0.0f;
-  if (probe) for (int n = 0; n < N; ++n) B[(size_t)n * K] = 1.0f;   // picks A[m][0]
   for (auto& v : B) v = rnd() / 8.0f;
+  if (probe) {
+    // Operand-rounding probe: D[m][n] = A[m][0] exactly as the tensor core reads it (B picks k = 0; everything else 0).
+    // A[m][0] carries all 13 sub-tf32 mantissa bits in varied patterns, both signs, several exponents.
+    for (auto& v : A) v = 0.0f;
+    for (auto& v : B) v = 0.0f;
+    for (int n = 0; n < N; ++n) B[(size_t)n * K] = 1.0f;
+    for (int m = 0; m < M; ++m) {
+      uint32_t bits = 0x3f800000u + ((uint32_t)(m % 7) << 23) + ((uint32_t)m * 0x9E3779B1u & 0x007fffffu);
+      if (m & 1) bits |= 0x80000000u;
+      if (m == 2) bits = 0x3f800000u | 0x1fffu;          // 1 + (2^13 - 1) ulp: truncation -> 1, nearest -> 1 + 2^-10
+      if (m == 3) bits = 0x3f800000u | 0x1000u;          // exactly half way
+      if (m == 4) bits = 0x00001000u;                    // the encoding of zero used by the pre-biased code layout
+      memcpy(&A[(size_t)m * K], &bits, 4);
+    }
+  }
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
       int j = k / 8, kk = k % 8;
@@ -187,7 +201,20 @@ int main(int argc, char** argv) {
   long long hc = hcs[0];
   printf("issue timing cg=%d ts=%d N=%d: %d MMAs issued in %lld cycles (%.1f each), commit %lld, all complete after %lld\n", cg, ts, N, rep * KS, hcs[1], (double)hcs[1] / (rep * KS), hcs[2], hcs[0]);
   if (rep > 1) printf("timing cg=%d ts=%d N=%d KS=%d rep=%d commit-every=%d : %.1f cycles per MMA\n", cg, ts, N, KS, rep, cgroup, (double)hc / ((double)rep * KS));
-  if (probe) { printf("rounding probe: A = 1 + 0.75*2^-11 (tf32 ulp 2^-10): D[0][0] = %.10f  (1.0 = truncation, 1.0009765625 = round-to-nearest)\n", D[0]); return 0; }
+  if (probe) {
+    long ntrunc = 0, nrna = 0, nother = 0;
+    for (int m = 0; m < M; ++m) {
+      uint32_t a, d;
+      memcpy(&a, &A[(size_t)m * K], 4); memcpy(&d, &D[(size_t)m * N], 4);
+      const uint32_t tr = a & 0xffffe000u, rn = (a + 0x1000u) & 0xffffe000u;
+      if (d == tr) ++ntrunc;
+      if (d == rn) ++nrna;
+      if (d != tr && d != rn) { ++nother; if (nother < 5) printf("  row %d: a=%08x d=%08x trunc=%08x rna=%08x\n", m, a, d, tr, rn); }
+    }
+    printf("operand probe ts=%d cg=%d: %d rows, D == truncate(A) on %ld, D == rna(A) on %ld, neither on %ld  => the tensor core %s its fp32 operand words\n",
+           ts, cg, M, ntrunc, nrna, nother, (ntrunc == M) ? "TRUNCATES" : (nrna == M ? "ROUNDS (rna)" : "does something else with"));
+    return ntrunc == M ? 0 : 3;
+  }
   double maxerr = 0; long bad = 0;
   for (size_t i = 0; i < D.size(); ++i) { double e = fabs((double)D[i] - R[i]); if (e > maxerr) maxerr = e; if (e > 1e-5) ++bad; }
   printf("selftest cg=%d ts=%d M=%d N=%d K=%d : max|err|=%.3e bad=%ld/%zu  %s\n", cg, ts, M, N, K, maxerr, bad, D.size(), bad ? "FAIL" : "PASS");

@@ -48,12 +48,18 @@ class Plan:
         self.coarse = tuple(lay.coarse)              # z (D,H,W)
         self.ndim, self.N, self.C, self.M, self.K, self.s = ndim, N, C, M, K, s
         self.dims = tuple(int(v) for v in dims)
+        self.Pfull = tuple(int(v) for v in P3)
         self.has_mask = bool(has_mask)
         n = ctypes.c_size_t()
-        _lib.check(self.lib.cdl_plan_workspace_bytes(handle, ctypes.byref(n)))
-        self.workspace_bytes = n.value
-        _lib.check(self.lib.cdl_plan_host_workspace_bytes(handle, ctypes.byref(n)))
-        self.host_workspace_bytes = n.value
+        # the workspace regions are prefixes of one another: reduce < step < forward < host (< host + z staging)
+        self._ws_bytes = {}
+        for kind, fn in (("reduce", self.lib.cdl_plan_reduce_workspace_bytes), ("step", self.lib.cdl_plan_step_workspace_bytes),
+                         ("forward", self.lib.cdl_plan_workspace_bytes), ("host", self.lib.cdl_plan_host_workspace_bytes_noz),
+                         ("host_z", self.lib.cdl_plan_host_workspace_bytes)):
+            _lib.check(fn(handle, ctypes.byref(n)))
+            self._ws_bytes[kind] = n.value
+        self.workspace_bytes = self._ws_bytes["forward"]
+        self.host_workspace_bytes = self._ws_bytes["host_z"]
         _lib.check(self.lib.cdl_plan_code_bytes(handle, ctypes.byref(n)))
         self.code_bytes = n.value
         self._ws = None
@@ -87,9 +93,14 @@ class Plan:
         _lib.check(self.lib.cdl_plan_launch_count(self.handle, ctypes.byref(n)))
         return n.value
 
-    def workspace(self, host=False):
-        need = self.host_workspace_bytes if host else self.workspace_bytes
+    def workspace(self, kind="forward", host=False):
+        """Device workspace large enough for `kind`: "reduce" (cdl_reduce_sums only), "step" (stepwise entry points),
+        "forward" (cdl_forward / cdl_denoise), "host" / "host_z" (cdl_denoise_host without / with z).  Grows on demand."""
+        if host:
+            kind = "host_z"
+        need = self._ws_bytes[kind]
         if self._ws is None or self._ws.numel() < need:
+            self._ws = None                          # release before growing (the forward workspace of a long clip is tens of GB)
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
@@ -110,6 +121,14 @@ class Plan:
         if key is not None and key == self._weights_key:
             return
         K = self.K
+        P = self.Pfull[-self.ndim:]
+        want = (self.M, self.C, *P)
+        if len(A) != K or len(B) != K or t.numel() != K * 2 * self.M:
+            raise ValueError(f"set_weights: expected {K} analysis and {K} synthesis banks and {K}x2x{self.M} thresholds")
+        for name, bank in (("A", A), ("B", B)):
+            for k, w in enumerate(bank):
+                if tuple(w.shape) != want:          # the library only sees raw pointers: a mismatch would read out of bounds
+                    raise ValueError(f"set_weights: {name}[{k}] has shape {tuple(w.shape)}, the plan needs {want}")
         A = [a.detach().to(self.device, torch.float32).contiguous() for a in A]
         B = [b.detach().to(self.device, torch.float32).contiguous() for b in B]
         t = t.detach().to(self.device, torch.float32).reshape(K, 2, self.M).contiguous()
@@ -120,10 +139,15 @@ class Plan:
         self._weights_key = key
 
     # whole forward ------------------------------------------------------------------------------
-    def denoise(self, y, mask=None, c=None, z_out=None):
-        """y (N,C,dims) -> (xhat like y, z).  c: (N,) fp32 sigma/255 or None."""
+    def denoise(self, y, mask=None, c=None, z_out=None, want_z=True):
+        """y (N,C,dims) -> (xhat like y, z).  c: (N,) fp32 sigma/255 or None.  want_z=False: z is not converted to
+        (N,M,coarse) and None is returned for it (the code of a long clip is tens of GB)."""
+        if tuple(y.shape) != self.in_shape or (mask is not None and tuple(mask.shape) != self.in_shape):
+            raise ValueError(f"denoise: input shape {tuple(y.shape)} does not match the plan's {self.in_shape}")
         xhat = torch.empty(self.in_shape, dtype=torch.float32, device=self.device)
-        z = z_out if z_out is not None else torch.empty(self.z_shape, dtype=torch.float32, device=self.device)
+        z = None
+        if want_z:
+            z = z_out if z_out is not None else torch.empty(self.z_shape, dtype=torch.float32, device=self.device)
         ws = self.workspace()
         _lib.check(self.lib.cdl_denoise(self.handle, _ptr(y), _ptr(mask), _ptr(c), _ptr(xhat), _ptr(z), _ptr(ws), _stream()),
                    "cdl_denoise")
@@ -131,7 +155,7 @@ class Plan:
 
     def denoise_host(self, y_host, xhat_host, mask_host=None, c_host=None, z_host=None):
         """Pinned host buffers in, pinned host buffers out; asynchronous on the current stream."""
-        ws = self.workspace(host=True)
+        ws = self.workspace("host" if z_host is None else "host_z")
         _lib.check(self.lib.cdl_denoise_host(self.handle, _ptr(y_host), _ptr(mask_host), _ptr(c_host), _ptr(xhat_host),
                                              _ptr(z_host), _ptr(ws), _stream()), "cdl_denoise_host")
 
@@ -155,12 +179,12 @@ class Plan:
         mp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device) if self.has_mask else None
         mean = torch.empty(self.N, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.cdl_preprocess(self.handle, _ptr(y), _ptr(mask), _ptr(yp), _ptr(mp), _ptr(mean),
-                                           _ptr(self.workspace()), _stream()), "cdl_preprocess")
+                                           _ptr(self.workspace("step")), _stream()), "cdl_preprocess")
         return yp, mp, mean
 
     def reduce_sums(self, y, mask=None):
         sums = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.cdl_reduce_sums(self.handle, _ptr(y), _ptr(mask), _ptr(sums), _ptr(self.workspace()), _stream()),
+        _lib.check(self.lib.cdl_reduce_sums(self.handle, _ptr(y), _ptr(mask), _ptr(sums), _ptr(self.workspace("reduce")), _stream()),
                    "cdl_reduce_sums")
         return sums
 
@@ -178,13 +202,37 @@ class Plan:
 
     def analysis_step(self, k, r, z, c=None, first=False):
         _lib.check(self.lib.cdl_analysis_step(self.handle, k, int(first), _ptr(r), _ptr(c), _ptr(z),
-                                              _ptr(self.workspace()), _stream()), "cdl_analysis_step")
+                                              _ptr(self.workspace("step")), _stream()), "cdl_analysis_step")
         return z
 
     def synthesis_step(self, k, z, out, yp=None, mask_p=None, residual=True):
         _lib.check(self.lib.cdl_synthesis_step(self.handle, k, int(residual), _ptr(z), _ptr(yp), _ptr(mask_p), _ptr(out),
-                                               _ptr(self.workspace()), _stream()), "cdl_synthesis_step")
+                                               _ptr(self.workspace("step")), _stream()), "cdl_synthesis_step")
         return out
+
+    # temporal slabs across GPUs ----------------------------------------------------------------------
+    @property
+    def halo_bytes(self):
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.cdl_halo_bytes(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def analysis_step_halo(self, k, r, z, c, recv_prev, recv_next, yp):
+        _lib.check(self.lib.cdl_analysis_step_halo(self.handle, k, _ptr(r), _ptr(c), _ptr(z), _ptr(recv_prev), _ptr(recv_next),
+                                                   _ptr(yp), _ptr(self.workspace("step")), _stream()), "cdl_analysis_step_halo")
+        return z
+
+    def halo_add(self, r, recv_prev, recv_next, yp=None):
+        _lib.check(self.lib.cdl_halo_add(self.handle, _ptr(r), _ptr(recv_prev), _ptr(recv_next), _ptr(yp), _stream()), "cdl_halo_add")
+
+    def comm_allreduce(self, comm, sums):
+        _lib.check(self.lib.cdl_comm_allreduce_f64(comm.handle, _ptr(sums), sums.numel(), _stream()), "cdl_comm_allreduce_f64")
+
+    def forward_sharded(self, comm, yp, c, code, r, halo_ws):
+        """cdl_forward_sharded: all K iterations + D z of this rank's slab; r returns xphat on the resident frames."""
+        _lib.check(self.lib.cdl_forward_sharded(self.handle, comm.handle if comm is not None else None, _ptr(yp), _ptr(c),
+                                                _ptr(code), _ptr(r), _ptr(halo_ws), _ptr(self.workspace("step")), _stream()),
+                   "cdl_forward_sharded")
 
     def forward(self, yp, mask_p=None, c=None):
         z = torch.empty(self.z_shape, dtype=torch.float32, device=self.device)

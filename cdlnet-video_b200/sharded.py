@@ -38,6 +38,10 @@ def slab_geometry(D: int, Pd: int, s: int, world: int, rank: int):
         raise ValueError("fewer coarse frames than ranks")
     q0, q1 = slab_bounds(Qd, world, rank)
     h = Pd // 2
+    if world > 1 and Pd - s > 0 and h - s + 1 <= 0:
+        # e.g. Pd = 3, s = 2: the seam overlap (Pd - s = 1 frame) lies entirely in the NEXT rank's front halo, so the
+        # symmetric exchange below would have one side with nothing to send or receive - not implemented
+        raise ValueError(f"temporal sharding needs Pd//2 - s + 1 > 0 (got Pd={Pd}, s={s})")
     hf = h if rank > 0 else 0
     hb = (h - s + 1) if rank < world - 1 else 0
     if min(b - a for a, b in (slab_bounds(Qd, world, r) for r in range(world))) * s < Pd:
@@ -71,6 +75,13 @@ class PlanOps:
 
     def analysis(self, k, r, code, c, first):
         self.plan.analysis_step(k, r, code, c, first=first)
+
+    def analysis_halo(self, k, r, code, c, recv_prev, recv_next, yp):
+        """analysis step on r + the neighbours' seam partials (+ yp back): the sum is fused into the step's rounding pass"""
+        self.plan.analysis_step_halo(k, r, code, c, recv_prev, recv_next, yp)
+
+    def halo_add(self, r, recv_prev, recv_next, yp=None):
+        self.plan.halo_add(r, recv_prev, recv_next, yp)
 
     def synthesis(self, k, code, out, yp, residual):
         self.plan.synthesis_step(k, code, out, yp, None, residual=residual)
@@ -137,6 +148,16 @@ class SlabRank:
     def ana(self, k):
         self.ops.analysis(k, self.r, self.code, self.c, False)
 
+    def halo_ana(self, k, recv_prev, recv_next):
+        """add_halo + ana; one fused pass where the operators offer it (the CUDA plan), two steps otherwise (oracle ops)"""
+        if hasattr(self.ops, "analysis_halo") and self._residual:
+            rp = recv_prev.contiguous() if recv_prev is not None else None
+            rn = recv_next.contiguous() if recv_next is not None else None
+            self.ops.analysis_halo(k, self.r, self.code, self.c, rp, rn, self.yp)
+        else:
+            self.add_halo(recv_prev, recv_next)
+            self.ana(k)
+
     def finish(self):
         """After the final synth(0, residual=False) + add_halo: crop to the owned frames."""
         x = self.ops.postprocess(self.r, self.mean)
@@ -166,9 +187,11 @@ def run_lockstep(ranks, y_slabs, c):
         r.first()
     K = ranks[0].K
     for k in range(1, K):
-        exchange([r.synth(k, True) for r in ranks])
-        for r in ranks:
-            r.ana(k)
+        pairs = [r.synth(k, True) for r in ranks]
+        snap_h = [p[0].clone() if p[0] is not None else None for p in pairs]
+        snap_t = [p[1].clone() if p[1] is not None else None for p in pairs]
+        for i, r in enumerate(ranks):
+            r.halo_ana(k, snap_t[i - 1] if i > 0 else None, snap_h[i + 1] if i + 1 < len(ranks) else None)
     exchange([r.synth(0, False) for r in ranks])
     outs = [r.finish() for r in ranks]
     return torch.cat([o[0] for o in outs], dim=2), torch.cat([o[1] for o in outs], dim=2)
@@ -208,19 +231,54 @@ def run_distributed(rank_state, y_slab, c, xch: DistExchange):
     rank_state.first()
     for k in range(1, rank_state.K):
         head, tail = rank_state.synth(k, True)
-        rank_state.add_halo(*xch.halo(head, tail))
-        rank_state.ana(k)
+        rank_state.halo_ana(k, *xch.halo(head, tail))
     head, tail = rank_state.synth(0, False)
     rank_state.add_halo(*xch.halo(head, tail))
     return rank_state.finish()
 
 
+class NativeComm:
+    """libcdl_b200's own NCCL communicator (cdl_comm_create): rank 0 draws the ncclUniqueId and the process group that
+    torchrun set up carries its 128 bytes to the other ranks."""
+
+    def __init__(self, rank, world, device, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        dev = torch.device(device)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev if dist.get_backend(group) == "nccl" else "cpu")
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _lib.check(self.lib.cdl_comm_unique_id(buf), "cdl_comm_unique_id")
+            idt.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(idt, src=0, group=group)
+        raw = bytes(idt.cpu().numpy().tobytes())
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.cdl_comm_create(ctypes.byref(self.handle), raw, rank, world, dev.index or 0), "cdl_comm_create")
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cdl_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedVideoDenoiser:
-    """Convenience wrapper: one long clip (N,1,D,H,W) over `world` GPUs, one process per GPU.
+    """One long clip (N,1,D,H,W) over `world` GPUs, one process per GPU (BASELINE config 5).
 
         den = ShardedVideoDenoiser(net, clip_shape, rank, world, device)
         xhat_owned, z_owned = den(y_slab, sigma)          # y_slab = clip frames den.geo["f0"]:den.geo["f1"]
-    """
+
+    The whole forward of a rank runs inside the library (cdl_forward_sharded): K iterations, per-iteration NCCL
+    neighbour exchange of the Pd - s seam frames, seam sums fused into the analysis step.  world == 1 runs the same
+    entry point without a communicator (the one-GPU point of a strong-scaling curve)."""
 
     def __init__(self, net, clip_shape, rank, world, device, precision="tf32", group=None):
         from .plan import Plan
@@ -234,12 +292,47 @@ class ShardedVideoDenoiser:
         sum_plan = Plan(3, N, C, net.M, 1, (net.s * (g["q1"] - g["q0"]), H, W), P3, net.s, precision="fp32", device=dev_index)
         A, B = net._filter_banks()
         plan.set_weights(A, B, net.t)
-        self.net, self.plan = net, plan
+        self.net, self.plan, self.sum_plan = net, plan, sum_plan
         self.state = SlabRank(PlanOps(plan, sum_plan), g, net.K, net.s)
         self.group, self.xch = group, None          # the exchange is created on first use (needs an initialised process group)
-        self.world = world
+        self.rank, self.world = rank, world
+        self.comm = None
+        self.code = self.r = self.halo = None
+
+    # -- native route ---------------------------------------------------------------------------------
+    def _buffers(self):
+        if self.code is None:
+            self.code = self.plan.new_code()
+            self.r = torch.empty(self.plan.fine_shape, dtype=torch.float32, device=self.plan.device)
+            self.halo = torch.empty(2 * self.plan.halo_bytes // 4, dtype=torch.float32, device=self.plan.device)
+        if self.world > 1 and self.comm is None:
+            self.comm = NativeComm(self.rank, self.world, self.plan.device, self.group)
+
+    def forward_resident(self, y_slab, sigma=None, want_z=False):
+        """y_slab on the device -> (xhat of the owned frames, z of the owned coarse frames or None)."""
+        self._buffers()
+        plan, g = self.plan, self.geo
+        c = self.net._c_vector(sigma, y_slab.shape[0], y_slab.device)
+        owned = y_slab[:, :, g["hf"]:y_slab.shape[2] - g["hb"]]
+        sums = self.sum_plan.reduce_sums(owned.contiguous())
+        if self.world > 1:
+            plan.comm_allreduce(self.comm, sums)
+        mean = plan.mean_from_sums(sums)
+        yp = plan.center_pad(y_slab.contiguous(), mean)[0]
+        plan.forward_sharded(self.comm, yp, c, self.code, self.r, self.halo)
+        x = plan.postprocess(self.r, mean)
+        xhat = x[:, :, g["hf"]:x.shape[2] - g["hb"]]
+        return xhat, (plan.export_code(self.code) if want_z else None)
+
+    def denoise_host(self, y_host_slab, xhat_host_owned, sigma=None):
+        """Pinned host slab in, owned frames of xhat out into a pinned host buffer; asynchronous on the current stream."""
+        y = y_host_slab.to(self.plan.device, non_blocking=True)
+        xhat, _ = self.forward_resident(y, sigma)
+        xhat_host_owned.copy_(xhat, non_blocking=True)
 
     def __call__(self, y_slab, sigma=None):
+        if y_slab.is_cuda:
+            return self.forward_resident(y_slab, sigma, want_z=True)
         c = self.net._c_vector(sigma, y_slab.shape[0], y_slab.device)
         if self.world == 1:
             st = self.state

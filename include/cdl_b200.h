@@ -26,6 +26,7 @@ extern "C" {
 
 #define CDL_ABI_VERSION 1
 #define CDL_CUDA_ERROR_BASE 1000
+#define CDL_NCCL_ERROR_BASE 2000   /* + ncclResult_t */
 
 enum cdl_status {
   CDL_OK = 0,
@@ -36,7 +37,8 @@ enum cdl_status {
   CDL_ERR_NO_WEIGHTS = -5,  /* cdl_set_weights has not been called                          */
   CDL_ERR_NO_DEVICE = -6,   /* no CUDA device / not an sm_100 device                        */
   CDL_ERR_RANGE = -7,       /* layer index or slab range out of bounds                      */
-  CDL_ERR_WORKSPACE = -8    /* workspace NULL or too small                                  */
+  CDL_ERR_WORKSPACE = -8,   /* workspace NULL or too small                                  */
+  CDL_ERR_NO_NCCL = -9      /* libnccl.so.2 not loadable (only the multi-GPU entry points need it) */
 };
 
 enum cdl_precision {
@@ -85,6 +87,11 @@ int  cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* desc);
 void cdl_plan_destroy(cdl_plan_t* plan);
 int  cdl_plan_layout(const cdl_plan_t* plan, cdl_layout_t* out);
 int  cdl_plan_workspace_bytes(const cdl_plan_t* plan, size_t* out);
+/* The workspace regions are ordered so that smaller uses are prefixes of the full workspace: a driver that only calls
+ * cdl_reduce_sums / cdl_mean_from_sums allocates cdl_plan_reduce_workspace_bytes, one that only calls the stepwise entry
+ * points (cdl_analysis_step, cdl_synthesis_step, cdl_preprocess) cdl_plan_step_workspace_bytes.                      */
+int  cdl_plan_reduce_workspace_bytes(const cdl_plan_t* plan, size_t* out);
+int  cdl_plan_step_workspace_bytes(const cdl_plan_t* plan, size_t* out);
 /* Effective precision after plan creation (a TF32 request falls back to FP32 kernels for
  * geometries the tensor-core path does not cover; never to the CPU).                          */
 int  cdl_plan_precision(const cdl_plan_t* plan);
@@ -122,7 +129,8 @@ int cdl_synthesis_step(cdl_plan_t* plan, int k, int residual, const float* code,
  * tensor-core path uses it; cdl_forward always does this on its own buffer.  enable = 0 restores const semantics.    */
 int cdl_plan_set_rearm(cdl_plan_t* plan, int enable);
 
-/* All K iterations + D z:  z (N,M,coarse) and xphat (N,C,fine) out.                              */
+/* All K iterations + D z:  z (N,M,coarse) and xphat (N,C,fine) out.  z may be NULL: the code then stays in the
+ * workspace and the pass that converts it to (N,M,coarse) is skipped.                             */
 int cdl_forward(cdl_plan_t* plan, const float* yp, const float* mask_p, const float* c, float* z, float* xphat, void* workspace, void* stream);
 /* post_process / post_process_3d (model/utils.py:24-33, 89-98): crop the stride padding, add the mean. */
 int cdl_postprocess(cdl_plan_t* plan, const float* xphat, const float* mean, float* xhat, void* stream);
@@ -133,8 +141,31 @@ int cdl_denoise(cdl_plan_t* plan, const float* y, const float* mask, const float
  * is non-NULL) out, on `stream`.  The device staging area lives in `workspace` (see
  * cdl_plan_host_workspace_bytes).  This is the end-to-end entry bench.py's `e2e` times.            */
 int cdl_plan_host_workspace_bytes(const cdl_plan_t* plan, size_t* out);
+int cdl_plan_host_workspace_bytes_noz(const cdl_plan_t* plan, size_t* out);   /* enough when z_host == NULL */
 int cdl_denoise_host(cdl_plan_t* plan, const float* y_host, const float* mask_host, const float* c_host,
                      float* xhat_host, float* z_host, void* workspace, void* stream);
+
+/* ---- temporal slabs across GPUs (the reference has no counterpart: analyze3d.py:62,105-106 chops a
+ * clip into independent 16-frame windows instead).  One process per GPU; rank r's plan is a slab plan (halo_front /
+ * halo_back above).  Per iteration the ranks exchange the Pd - s seam frames of their partial B z with their ring
+ * neighbours (NCCL P2P send/recv, grouped) and add them; the sum is fused into the analysis step's rounding pass.
+ * NCCL is dlopen'ed (libnccl.so.2) on first use.                                                                     */
+typedef struct cdl_comm cdl_comm_t;
+int  cdl_comm_unique_id(void* id128);                         /* rank 0: 128-byte ncclUniqueId to hand to every rank */
+int  cdl_comm_create(cdl_comm_t** out, const void* id128, int rank, int nranks, int device);
+void cdl_comm_destroy(cdl_comm_t* comm);
+int  cdl_comm_allreduce_f64(cdl_comm_t* comm, double* buf, size_t n, void* stream);   /* the global mean's sums */
+int  cdl_halo_bytes(const cdl_plan_t* plan, size_t* out);     /* bytes of ONE receive buffer: (N, Pd - s, Fh, Fw) fp32 */
+int  cdl_halo_exchange(cdl_plan_t* plan, cdl_comm_t* comm, const float* r, float* recv_prev, float* recv_next, void* stream);
+/* analysis step on r + received seam partials (+ yp back on the seams when yp != NULL: residual mode, both partials
+ * carry -yp); recv_* as written by cdl_halo_exchange, ignored on a side without a halo                                */
+int  cdl_analysis_step_halo(cdl_plan_t* plan, int k, const float* r, const float* c, float* code, const float* recv_prev,
+                            const float* recv_next, const float* yp, void* workspace, void* stream);
+int  cdl_halo_add(cdl_plan_t* plan, float* r, const float* recv_prev, const float* recv_next, const float* yp, void* stream);
+/* All K iterations + D z of one rank's slab; r (N,C,Fd,Fh,Fw) returns xphat on the resident frames; halo_ws holds two
+ * receive buffers (2 x cdl_halo_bytes); workspace >= cdl_plan_step_workspace_bytes.  comm may be NULL without halos.  */
+int  cdl_forward_sharded(cdl_plan_t* plan, cdl_comm_t* comm, const float* yp, const float* c, float* code, float* r,
+                         void* halo_ws, void* workspace, void* stream);
 
 /* Number of kernels launched by this plan since creation (bench.py's gpu_launches).               */
 int cdl_plan_launch_count(const cdl_plan_t* plan, uint64_t* out);

@@ -55,3 +55,42 @@ def test_nccl_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SHARDED_OK" in out.stdout
+
+
+def test_lockstep_slabs_cfg5_hyperparameters_vs_oracle():
+    """BASELINE config 5's network (CDLNetVideo K=30, M=169, 7x7x7, s=2; SURVEY 8(d) weights and thresholds) on a
+    64 x 96 x 128 clip split into 4 temporal slabs (16 fine frames each + halos, lock step on one GPU): the sharded
+    tcgen05 forward must agree with the unsharded one AND with the CPU oracle within the 1e-4 bar."""
+    import bench
+    import cdl_oracle as O
+    d = torch.device("cuda", 0)
+    K, M = bench.CFG["K"], bench.CFG["M"]
+    D, H, W = 64, 96, 128
+    A, B, u = bench.synthetic_weights(torch, d)
+    clean, y = bench.synthetic_clip(torch, 1, seed=5, device=d, shape=(D, H, W))
+    net = cb.CDLNetVideo(K=K, M=M, P=7, s=2, C=1, adaptive=True, init=False)
+    with torch.no_grad():
+        for k in range(K):
+            net.A[k].weight.copy_(A[k]); net.B[k].weight.copy_(B[k])
+    net = net.cuda().eval()
+    net.precision = "tf32"
+    t = bench.calibrate_thresholds(torch, A, B, u, y[:, :, :16], d)
+    with torch.no_grad():
+        net.t.copy_(t.reshape(net.t.shape))
+        xu, zu = net(y, bench.SIGMA)
+    assert net._last_plan.precision == "tf32"
+    world = 4
+    ranks, slabs = [], []
+    for r in range(world):
+        den = sharded.ShardedVideoDenoiser(net, tuple(y.shape), r, world, d, precision="tf32")
+        ranks.append(den.state)
+        slabs.append(y[:, :, den.geo["f0"]:den.geo["f1"]].contiguous())
+    c = torch.full((1,), bench.SIGMA / 255.0, device=d)
+    xs, zs = sharded.run_lockstep(ranks, slabs, c)
+    xr, zr, *_ = O.forward_t(y.cpu(), [a.cpu() for a in A], [b.cpu() for b in B], t.cpu().reshape(K, 2, M, 1, 1, 1), 2, bench.SIGMA, True, 1)
+    e_su = (xs - xu).abs().max().item()
+    e_so = (xs.cpu() - xr).abs().max().item()
+    e_uo = (xu.cpu() - xr).abs().max().item()
+    print(f"cfg5-like {D}x{H}x{W}, 4 slabs: sharded vs unsharded {e_su:.3e}; sharded vs oracle {e_so:.3e}; unsharded vs oracle {e_uo:.3e}; "
+          f"nnz {float((zr != 0).float().mean()):.3f}")
+    assert e_so <= 1e-4 and e_uo <= 1e-4 and e_su <= 1e-4, (e_su, e_so, e_uo)
