@@ -19,7 +19,6 @@
 #include "cdl_tc2_analysis.cuh"
 #include "cdl_tc2_analysis_x3.cuh"
 #include "cdl_tc2_synthesis.cuh"
-#include "cdl_tc2_synthesis_v2.cuh"
 
 using namespace cdl;
 
@@ -67,6 +66,22 @@ static int make_fine_tmap(CUtensorMap* out, const float* base, const Geo& g, int
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CDL_OK : CDL_ERR_UNSUPPORTED;
+}
+
+// code of the video tensor-core path viewed as (rows, groups per row, 1408 floats per group): a box is one A-ring chunk
+// of the synthesis kernel, 4 chunks of 4 subbands (512 contiguous bytes) x 16 groups of one row; groups beyond the row
+// and rows beyond the tensor read as zero
+static int make_code_tmap(CUtensorMap* out, const float* code, const Geo& g) {
+  const cuuint64_t G = (cuuint64_t)tc::code_groups_per_row(g.Qw);
+  const cuuint64_t rows = (cuuint64_t)g.N * g.Qd * g.Qh;
+  const cuuint64_t gdim[3] = {(cuuint64_t)tc::kCodeGroup, G, rows};
+  const cuuint64_t gstr[2] = {(cuuint64_t)tc::kCodeGroup * 4, G * tc::kCodeGroup * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)(tc::kSChunkK4 * tc::kCodeChunk), (cuuint32_t)tc::kSGroups, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(code), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CDL_OK : CDL_ERR_UNSUPPORTED;
 }
@@ -120,8 +135,7 @@ struct cdl_plan {
   size_t wA2_layer;
   size_t tc2_smem;
   bool tc2_syn;        // residual synthesis on the tensor cores too (cdl_tc2_synthesis.cuh)
-  bool tc2_ana_x3;     // candidate 3-term (hi/lo) analysis (cdl_tc2_analysis_x3.cuh), opt-in with CDL_TC2D_ANA=3; not yet validated on hardware
-  bool tc2_syn_v2;     // candidate col2im (cdl_tc2_synthesis_v2.cuh), opt-in with CDL_TC2D_SYN=2; not yet validated on hardware
+  bool tc2_ana_x3;     // CDL_PREC_TF32X3: 3-term (hi/lo) analysis (cdl_tc2_analysis_x3.cuh)
   bool tc2_maskpass;   // JDD mask applied by an image pass after the scatter-add instead of inside the footprint flush
   float* wB2;          // [K][Ng/8][176*8] tf32 filters in UMMA layout
   size_t wB2_layer;
@@ -338,17 +352,16 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   const bool tc2_geom = !nd3 && Ph == 7 && Pw == 7 && s == 1 && d->C <= tc2::kMaxC && d->M <= tc2::kNMax && (L.fine[2] % 4) == 0;
   // CDL_TC2D: 0 = off (fp32 CUDA-core kernels), 1 = tensor-core analysis only, 2 (default) = analysis + residual synthesis
   const int tc2_mode = getenv("CDL_TC2D") ? atoi(getenv("CDL_TC2D")) : 2;
-  if (d->precision == CDL_PREC_TF32 && tc2_geom && tc2_mode != 0) {
+  if ((d->precision == CDL_PREC_TF32 || d->precision == CDL_PREC_TF32X3) && tc2_geom && tc2_mode != 0) {
     p->tc2_ana = true;
     p->tc2_syn = tc2_mode >= 2;
-    p->tc2_ana_x3 = getenv("CDL_TC2D_ANA") && atoi(getenv("CDL_TC2D_ANA")) == 3;
-    p->tc2_syn_v2 = p->tc2_syn && getenv("CDL_TC2D_SYN") && atoi(getenv("CDL_TC2D_SYN")) == 2;
+    p->tc2_ana_x3 = d->precision == CDL_PREC_TF32X3;       // 3-term split analysis (cdl_tc2_analysis_x3.cuh)
     // JDD mask as one image pass after the scatter-add (default; measured 5.5 vs 10.0 ms per synthesis on config 3) or,
     // with CDL_TC2D_MASKPASS=0, inside the footprint flush
     p->tc2_maskpass = getenv("CDL_TC2D_MASKPASS") ? atoi(getenv("CDL_TC2D_MASKPASS")) != 0 : true;
     p->tc2_Ng = round_up(d->M, 16);
     p->tc2_smem = tc2::smem_layout(d->C, p->tc2_Ng).total;
-    p->precision_eff = CDL_PREC_TF32;
+    p->precision_eff = d->precision;
   }
 
   // ---- CUDA-core analysis configuration ----
@@ -432,7 +445,8 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     if ((e = cudaMalloc(&p->wAtc, p->wAtc_layer * g.K * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&p->wBtc, p->wBtc_layer * g.K * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&p->wBtc_lo, p->wBtc_layer * sizeof(float))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kAnaSmemBytes)) != cudaSuccess) {
       cdl_plan_destroy(p);
       return CDL_CUDA_ERROR_BASE + (int)e;
@@ -451,8 +465,6 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
                                   (int)tc2::syn_smem_bytes(tc2::kNMax))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis_x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::smem_layout_x3(tc2::kMaxC, tc2::kNMax).total)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)tc2::syn2_smem_bytes(tc2::kNMax))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::smem_layout(tc2::kMaxC, tc2::kNMax).total)) != cudaSuccess) {   // the limit is per function, not per plan
       cdl_plan_destroy(p);
@@ -857,37 +869,25 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.g = p->g;
     a.z = z; a.out = out;
     a.wpack = p->wBtc + (size_t)k * p->wBtc_layer;
-    a.tiles_w = ceil_div(p->g.Qw, tc::kTW);
-    a.tiles_h = ceil_div(p->g.Qh, 2 * tc::kTH);
-    a.ntiles = p->g.N * p->g.Qd * a.tiles_h * a.tiles_w;
+    a.tiles_w = ceil_div(p->g.Qw, tc::kSTileW);
+    a.nrows = (long long)p->g.N * p->g.Qd * p->g.Qh;
+    a.ntiles = a.nrows * a.tiles_w;
     a.dbg = g_tc_dbg;
     a.dbg_mode = p->dbg_mode;
-    a.a_lo = 0;
-    int pairs = p->sm_count / 2;
-    if (pairs > a.ntiles) pairs = a.ntiles;
-    {
-      // Units: (n, d-segment, h-tile, w-tile) columns of `seg` consecutive coarse frames; seg is the largest divisor
-      // of Qd that still leaves >= 4 units per CTA pair (load balance), because only the last tile of a unit flushes
-      // its whole 7-plane footprint.
-      const int cols = p->g.N * a.tiles_h * a.tiles_w;
-      int seg = 1;
-      for (int d = 1; d <= p->g.Qd; ++d)
-        if (p->g.Qd % d == 0 && (long long)cols * (p->g.Qd / d) >= 4LL * pairs) seg = d;
-      a.seg = seg; a.nseg = p->g.Qd / seg; a.nunits = cols * a.nseg;
-      if (pairs > a.nunits) pairs = a.nunits;
-    }
-    tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
+    long long pairs = p->sm_count / 2;
+    if (pairs > (a.ntiles + 1) / 2) pairs = (a.ntiles + 1) / 2;
+    const CUtensorMap* zmap;
+    { int rc = cached_tmap(p, z, -1, [&](CUtensorMap* m) { return make_code_tmap(m, z, p->g); }, &zmap); if (rc) return rc; }
+    tc::k_tc_synthesis<false><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);
     CDL_LAUNCH_CHECK(p);
     if (!residual && k == 0) {
       // Final dictionary synthesis xphat = D z (model/net.py:90,210): its tf32 rounding lands directly on xhat and
       // dominates the output error (measured: 7e-5 of 8e-5), so the two dropped cross terms are added back:
       //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)       (the scatter-add accumulates the three launches)
-      a.a_lo = 1;
-      tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
+      tc::k_tc_synthesis<true><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);
       CDL_LAUNCH_CHECK(p);
-      a.a_lo = 0;
       a.wpack = p->wBtc_lo;
-      tc::k_tc_synthesis<<<2 * pairs, tc::kThreads, tc::kSynSmemBytes, st>>>(a);
+      tc::k_tc_synthesis<false><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);
       CDL_LAUNCH_CHECK(p);
     }
     return CDL_OK;
@@ -916,8 +916,7 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.ntiles = p->g.N * a.tiles_h * a.tiles_w;
     int ctas = p->sm_count;
     if (ctas > a.ntiles) ctas = a.ntiles;
-    if (p->tc2_syn_v2) tc2::k_tc2_synthesis_v2<<<ctas, tc2::kSThreads, tc2::syn2_smem_bytes(a.Kg), st>>>(a);
-    else tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
+    tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
     CDL_LAUNCH_CHECK(p);
     if (maskpass) {
       tc2::k_mask_residual<<<(int)blocks, 256, 0, st>>>(out, mask_p, yp, n4);

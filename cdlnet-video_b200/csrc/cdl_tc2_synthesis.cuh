@@ -15,23 +15,23 @@
 //   * B operand = the filter bank, resident: [K/8 steps][176 rows (c,th,tw8)][8 subbands] = 45 KB; column
 //     (c*7 + th)*8 + tw of the accumulator, tw = 7 is padding (every (c,th) row is one tcgen05.ld of 8 columns).
 //   * Accumulators double buffered: 2 x 176 + 2 x 64 = 480 of 512 TMEM columns.
-//   * col2im (4 warps = the 4 tile rows): the (c,th) rows are walked in lock step - at step t warp r handles
-//     th = (t + r) mod 7, which lands on footprint row r + th = t + 2r (- 7 when wrapped): distinct for the four
-//     warps (tests/test_tc2_operand_cpu.py), a named barrier between steps - no shared-memory atomics.  Inside a warp
-//     the 7 tw values are combined across lanes with rotate-shuffles, so that every footprint column is
-//     read-modify-written by exactly one lane (own column L, lanes 0..5 also the spill column 32 + L).
-//     The finished 10 x 38 x C footprint is added to `out` with red.global.add (times the mask in JDD mode) and cleared.
+//   * col2im (4 warps = the 4 tile rows), WRITE-ONCE PRIVATE FOOTPRINTS (round 2; the round-1 kernel walked the (c,th)
+//     rows in lock step with a named barrier per step and read-modify-wrote one shared footprint: 2.67 ms per launch on
+//     config 4, this one 2.17 ms).  Warp r owns a private buffer priv[r][(c,th)][40]: row (c,th) of it receives exactly
+//     one value per column and tile (columns 0..31 from the lanes' own sums, 32..37 from the spill sums of lanes 0..5),
+//     so it is WRITTEN, not accumulated: no read-modify-write, no clearing, no ordering between warps.  Inside a warp
+//     the 7 tw values are combined across lanes with rotate-shuffles; the accumulator is drained in 32-column
+//     tcgen05.ld's (four (c,th) rows each) with the next load in flight.
+//   * The overlap-add moves into the flush: out[c, h0-3+y, w0-3+x] += sum_{r = max(0,y-6)}^{min(3,y)} priv[r][c, y-r][x]
+//     (at most 4 terms, times the mask in JDD flush mode), executed by the eight PRODUCER warps one tile behind on a
+//     double-buffered priv (2 x 13.4 KB), with red.global.add.
 //   * JDD mask: by default `out` starts from zero and one image pass (k_mask_residual) forms mask * out - yp after
-//     the scatter-add; with CDL_TC2D_MASKPASS=0 `out` starts from -yp and the flush multiplies by the mask (slower:
-//     the mask loads sit on the flush's critical path, 10.0 vs 5.5 ms per launch on config 3).
-//   * Measured (B200): config 4 (64 x 3 x 512^2, M = 64) 2.67 ms per launch, config 3 (32 x 3 x 1024^2, mask) 5.46 ms
-//     (fp32 CUDA-core kernel: 15.2 / 30.4 ms); bit-exact against it on exactly representable data.  The col2im warps
-//     (tcgen05.ld + 6 shuffles + lock-step barrier per (c,th) row), not the tensor pipe or HBM, set the pace.
+//     the scatter-add; with CDL_TC2D_MASKPASS=0 `out` starts from -yp and the flush multiplies by the mask.
 //   * Only the RESIDUAL synthesis runs here; the final dictionary synthesis D z (its rounding would land directly on
 //     xhat) stays on the exact fp32 CUDA-core kernel.
 //
-// Warp roles (416 threads): warps 0-7 producers (two per TMEM lane quadrant, half of the subbands each), warps 8-11
-// col2im + flush, warp 12 MMA issue + TMEM alloc.
+// Warp roles (416 threads): warps 0-7 producers + flush (two per TMEM lane quadrant, half of the subbands each),
+// warps 8-11 col2im, warp 12 MMA issue + TMEM alloc.
 #pragma once
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
@@ -61,9 +61,6 @@ struct Syn2Params {
 };
 
 __host__ __device__ inline uint32_t syn_b_bytes(int Kg) { return (uint32_t)(Kg / 8) * kSN * 32u; }
-__host__ __device__ inline uint32_t syn_smem_bytes(int Kg) {
-  return align128(syn_b_bytes(Kg)) + (uint32_t)(kMaxC * kFY * kFPitch * 4) + 128u;
-}
 
 // filters (M,C,7,7) [ConvTranspose2d weight (in = M, out = C, th, tw)] -> B[n = (c*7 + th)*8 + tw, k = m], UMMA K-major
 __global__ void k_pack_tc2_synthesis(const float* __restrict__ w, float* __restrict__ out, int M, int C, int Kg) {
@@ -96,35 +93,46 @@ __device__ __forceinline__ void syn_tile_coords(const Syn2Params& p, int tile, i
   h0 = th * kSTH; w0 = tw * kSTW;
 }
 
+constexpr int kPrivRows = kMaxC * kP;                       // 21 (c,th) rows per warp
+constexpr int kPrivWarp = kPrivRows * kFPitch;              // floats per warp
+constexpr int kPrivBuf = kSColWarps * kPrivWarp;            // floats per buffer (4 warps)
+
+__host__ __device__ inline uint32_t syn_smem_bytes(int Kg) {
+  return align128(syn_b_bytes(Kg)) + (uint32_t)(2 * kPrivBuf * 4) + 128u;
+}
+
 __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params p) {
   using namespace ptx;
   using tc2::mbar_wait;                        // bounded wait (traps instead of hanging)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t bbytes = syn_b_bytes(p.Kg);
   float* sB = reinterpret_cast<float*>(smem_raw);
-  float* sX = reinterpret_cast<float*>(smem_raw + align128(bbytes));                  // [C][10][40] footprint
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + align128(bbytes) + kMaxC * kFY * kFPitch * 4);
+  float* sP = reinterpret_cast<float*>(smem_raw + align128(bbytes));                  // [2][4 warps][21][40]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + align128(bbytes) + 2 * kPrivBuf * 4);
   uint64_t* wbar = bars + 0;
   uint64_t* afull = bars + 1;                  // [2] producers -> MMA
   uint64_t* aempty = afull + 2;                // [2] MMA commit -> producers
   uint64_t* dfull = aempty + 2;                // [2] MMA commit -> col2im
   uint64_t* dempty = dfull + 2;                // [2] col2im -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+  uint64_t* xfull = dempty + 2;                // [2] col2im -> producers: private footprints of a tile written
+  uint64_t* xfree = xfull + 2;                 // [2] producers -> col2im: flushed, buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = gridDim.x;
   const int ksteps = p.Kg >> 3;
+  const int nrows = kP * p.C;                  // (c,th) rows in use
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&afull[i], kSProdWarps); mbar_init(&aempty[i], 1);
       mbar_init(&dfull[i], 1); mbar_init(&dempty[i], kSColWarps);
+      mbar_init(&xfull[i], kSColWarps); mbar_init(&xfree[i], kSProdWarps);
     }
     fence_mbar_init();
   }
   if (warp == kSMmaWarp) { tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
-  for (int i = tid; i < kMaxC * kFY * kFPitch; i += kSThreads) sX[i] = 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -138,10 +146,9 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
   }
 
   if (warp < kSProdWarps) {
-    // ============================== producers: code tile -> tf32 -> TMEM A ring ==============================
-    // warp = quad + 4*half: TMEM lanes of tile row `quad`; subbands [half*Kg/2, (half+1)*Kg/2), 8 per tcgen05.st
+    // ============================== producers: code tile -> tf32 -> TMEM A ring; overlap-add + flush ==============================
     const int quad = warp & 3, half = warp >> 2;
-    const int nh = p.Kg >> 1;                                   // 8, 16, 24 or 32 subbands per thread
+    const int nh = p.Kg >> 1;
     const int m0 = half * nh;
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     const size_t plane = (size_t)p.H * p.W;
@@ -157,73 +164,22 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
       for (int j = 0; j < 32; ++j)
         rg[j] = ldg_f32_pred(base + (size_t)j * plane * 4, ok && j < nh && m0 + j < p.M);
     };
-    load_tile(blockIdx.x);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
-      const int b = it & 1, u = it >> 1;
-      uint32_t rt[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) rt[j] = tf32_rna_bits(rg[j]);
-      load_tile(tile + stride);                                 // the next tile's values are in flight during the hand-off
-      mbar_wait(&aempty[b], (u & 1) ^ 1);                      // the MMAs of tile it-2 have read this slot
-      tc_fence_after();
-      const uint32_t acol = lane_addr + (uint32_t)(kSColA + b * kNMax + m0);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (8 * q < nh) tmem_st8(acol + 8 * q, *reinterpret_cast<const uint32_t(*)[8]>(&rt[8 * q]));   // warp-uniform
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&afull[b]);
-    }
-  } else if (warp < kSMmaWarp) {
-    // ============================== col2im + flush ==============================
-    const int r = warp - kSProdWarps;                           // tile row = TMEM lane quadrant (warp & 3 == r)
-    const int ct = tid - 32 * kSProdWarps;                      // 0..127
-    const uint32_t lane_addr = tbase + ((uint32_t)(r * 32) << 16);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
-      const int b = it & 1, u = it >> 1;
+    // tile j of this CTA: out[c, h0-3+y, w0-3+x] += sum_r priv[r][c*7 + (y-r)][x]  over the rows r with 0 <= y-r <= 6
+    auto flush_tile = [&](int j) {
+      const int xb = j & 1;
       int n, h0, w0;
-      syn_tile_coords(p, tile, n, h0, w0);
-      mbar_wait(&dfull[b], u & 1);
-      tc_fence_after();
-      const uint32_t dcol = lane_addr + (uint32_t)(kSColD + b * kSN);
-      for (int c = 0; c < p.C; ++c) {
-#pragma unroll
-        for (int t = 0; t < kP; ++t) {
-          const int th = (t + r) % kP;
-          uint32_t v[8];
-          tmem_ld8(dcol + (uint32_t)((c * kP + th) * 8), v);
-          tmem_wait_ld();
-          if (c == p.C - 1 && t == kP - 1) {     // accumulator fully read: hand the TMEM buffer back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&dempty[b]);
-          }
-          named_bar_sync(2, 32 * kSColWarps);    // lock step: the four warps are on four different footprint rows
-          // Column x of the footprint row collects tap tw of lane x - tw.  A lane must not read-modify-write columns its
-          // neighbours also touch (no ordering between lanes), so the 7 taps are first combined across lanes with
-          // rotate-shuffles: lane L receives tap tw of lane (L - tw) mod 32 - for L >= tw that is a contribution to its
-          // own column L, for L < tw it comes from lane 32 + L - tw and belongs to the spill column 32 + L.
-          float own = __uint_as_float(v[0]), spill = 0.0f;
-#pragma unroll
-          for (int tw = 1; tw < kP; ++tw) {
-            const float w = __shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);
-            if (lane >= tw) own += w; else spill += w;
-          }
-          float* row = sX + (c * kFY + r + th) * kFPitch;
-          row[lane] += own;                                   // every column is touched by exactly one lane
-          if (lane < kP - 1) row[32 + lane] += spill;
-        }
-      }
-      named_bar_sync(2, 32 * kSColWarps);        // footprint complete
+      syn_tile_coords(p, (int)blockIdx.x + j * stride, n, h0, w0);
+      mbar_wait(&xfull[xb], (j >> 1) & 1);
+      const float* pv = sP + xb * kPrivBuf;
       const int nf = p.C * kFY * kFX;
-      for (int i = ct; i < nf; i += 32 * kSColWarps) {
+      for (int i = tid; i < nf; i += 32 * kSProdWarps) {
         const int x = i % kFX, y = (i / kFX) % kFY, c = i / (kFX * kFY);
-        float* cell = sX + (c * kFY + y) * kFPitch + x;
-        float v = *cell;
-        *cell = 0.0f;
+        float v = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kSTH; ++r) {
+          const int th = y - r;
+          if (th >= 0 && th < kP) v += pv[r * kPrivWarp + (c * kP + th) * kFPitch + x];
+        }
         const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;
         if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
           const size_t o = (((size_t)n * p.C + c) * p.H + gh) * p.W + gw;
@@ -231,14 +187,80 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
           red_add_f32(p.out + o, v);
         }
       }
-      // (the next tile's first accumulation step starts with the same named barrier: the cleared footprint is visible)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfree[xb]);
+    };
+    load_tile(blockIdx.x);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+      const int b = it & 1, u = it >> 1;
+      uint32_t rt[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rt[j] = tf32_rna_bits(rg[j]);
+      load_tile(tile + stride);
+      mbar_wait(&aempty[b], (u & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acol = lane_addr + (uint32_t)(kSColA + b * kNMax + m0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (8 * q < nh) tmem_st8(acol + 8 * q, *reinterpret_cast<const uint32_t(*)[8]>(&rt[8 * q]));
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[b]);
+      if (it > 0) flush_tile(it - 1);            // one tile behind: its col2im ran while this tile's A was produced
+    }
+    if (it > 0) flush_tile(it - 1);
+  } else if (warp < kSMmaWarp) {
+    // ============================== col2im: accumulator -> write-once private footprint ==============================
+    const int r = warp - kSProdWarps;
+    const uint32_t lane_addr = tbase + ((uint32_t)(r * 32) << 16);
+    // one (c,th) row: combine the 7 w-taps across lanes (lane L receives tap tw of lane (L - tw) mod 32: its own column for
+    // L >= tw, the spill column 32 + L otherwise) and WRITE columns L and 32 + L of the private row
+    auto put_row = [&](const uint32_t* v, float* row) {
+      float own = __uint_as_float(v[0]), spill = 0.0f;
+#pragma unroll
+      for (int tw = 1; tw < kP; ++tw) {
+        const float w = __shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);
+        if (lane >= tw) own += w; else spill += w;
+      }
+      row[lane] = own;
+      if (lane < kP - 1) row[32 + lane] = spill;
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
+      const int b = it & 1, u = it >> 1;
+      mbar_wait(&xfree[b], (u & 1) ^ 1);         // the flush of tile it-2 has read this private buffer
+      mbar_wait(&dfull[b], u & 1);
+      tc_fence_after();
+      const uint32_t dcol = lane_addr + (uint32_t)(kSColD + b * kSN);
+      float* priv = sP + b * kPrivBuf + r * kPrivWarp;
+      uint32_t ua[32], ub[32];
+      tmem_ld32(dcol, ua);                       // rows 0..3
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {              // groups of four (c,th) rows = 32 accumulator columns
+        uint32_t (&cur)[32] = (g & 1) ? ub : ua;
+        uint32_t (&nxt)[32] = (g & 1) ? ua : ub;
+        if (4 * g < nrows) {                     // warp-uniform
+          tmem_wait_ld();
+          if (g < 4) { if (4 * (g + 1) < nrows) tmem_ld32(dcol + 32 * (g + 1), nxt); }
+          else if (20 < nrows) tmem_ld8(dcol + 160, *reinterpret_cast<uint32_t(*)[8]>(&nxt[0]));   // row 20
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * g + q < nrows) put_row(&cur[8 * q], priv + (4 * g + q) * kFPitch);
+        }
+      }
+      if (20 < nrows) { tmem_wait_ld(); put_row(&ub[0], priv + 20 * kFPitch); }
+      tc_fence_before();                         // accumulator fully read, private footprint written
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&dempty[b]); mbar_arrive(&xfull[b]); }
     }
   } else {
     // ============================== MMA issue: whole warp converged, one elected lane issues ==============================
     mbar_wait(wbar, 0);
     const uint32_t idesc = make_idesc_tf32(128, kSN);
     const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
-    constexpr uint32_t kBStep = (kSN * 32) >> 4;                 // 16-byte units between consecutive k-steps of B
+    constexpr uint32_t kBStep = (kSN * 32) >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
       const int b = it & 1, u = it >> 1;
@@ -249,8 +271,8 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
       const uint32_t acol = tbase + (uint32_t)(kSColA + b * kNMax);
       for (int j = 0; j < ksteps; ++j)
         mma_tf32_ts_warp<1>(dcol, acol + 8 * j, bdesc0 + (uint64_t)j * kBStep, idesc, j != 0);
-      mma_commit_warp<1>(&aempty[b]);            // A slot reusable once these MMAs have read it
-      mma_commit_warp<1>(&dfull[b]);             // accumulator complete -> col2im
+      mma_commit_warp<1>(&aempty[b]);
+      mma_commit_warp<1>(&dfull[b]);
     }
     __syncwarp();
   }

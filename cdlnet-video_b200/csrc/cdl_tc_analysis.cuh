@@ -51,23 +51,35 @@ constexpr int kABoxPitch = 4800;                     // 19200 B: multiple of 128
 constexpr int kABuf = 2 * kABoxPitch;                // one tile: both h-parities
 constexpr int kColD = 0;                             // TMEM columns: D0 | D1
 
-// ---- internal code layout of the tensor-core path: "quad-blocked channels-last" ----
-// Along w, sites are grouped in fours of equal parity (qw = 8j + 2k + p, k = 0..3); a group stores its 176 subbands
-// as 22 blocks of [4 sites][8 subbands] = 128 bytes.  Both kernels keep one site per thread (= TMEM lane) and move 8
-// subbands per 256-bit access, so four neighbouring lanes always touch ONE full cache line: 8 lines per warp
-// instruction instead of 32 with a plain channels-last code (the L1 tag stage, not HBM, was the limit there).
-// Offset (floats) of subband block 0 of site (row, qw), row = (n*Qd + qd)*Qh + qh; block b sits 32*b floats further on.
-constexpr int kCodeBlk = 32;                        // floats between consecutive 8-subband blocks of one site
-constexpr int kCodeGroup = (kNA / 8) * kCodeBlk;    // 704 floats per group of 4 sites
+// ---- internal code layout of the tensor-core path: UMMA core matrices of 8 same-parity sites, pre-biased values ----
+// Along w, a row of sites is cut into blocks of 16; the 8 even and the 8 odd sites of a block form one GROUP each
+// (qw = 16 b + 2 i + p  ->  group 2 b + p, row i of the group).  A group stores its 176 subbands as 44 chunks of
+// [8 sites][4 subbands] = 128 bytes: exactly one K-major UMMA core matrix.  Consequences:
+//   * synthesis: a TMA box (c chunks x 16 groups) lands in shared memory as a legal no-swizzle K-major A operand
+//     (LBO = 128 B between the two chunks of a K-step, SBO = c * 128 B between groups) - the code goes from HBM to the
+//     tensor core without passing through a register (no producer warps);
+//   * analysis: a CTA owns the sites of one w-parity (overlapping-descriptor im2col), so the 8 lanes of a tile row hold
+//     the 8 rows of one group: a 128-bit access per lane fills a whole 128-byte line.
+// Values are stored PRE-BIASED: word = bits(z) + 0x1000.  tcgen05 kind::tf32 truncates its fp32 operand words to 19 bits,
+// and truncate(bits + 0x1000) == round-to-nearest(ties away)(z): the tensor core reads rna_tf32(z) straight from memory,
+// while the analysis epilogue recovers the exact fp32 z with one integer subtraction.  (Storing z itself rounded to tf32
+// costs 1.1-1.5e-4 on xhat; storing it unrounded and letting the tensor core truncate biases B z by 2^-11.)
+// Offset (floats) of subband 0 of site (row, qw), row = (n*Qd + qd)*Qh + qh; subband m sits (m >> 2) * 32 + (m & 3) further on.
+constexpr int kCodeChunk = 32;                      // floats per chunk: [8 sites][4 subbands]
+constexpr int kCodeK4 = kNA / 4;                    // 44 chunks per group
+constexpr int kCodeGroup = kCodeK4 * kCodeChunk;    // 1408 floats per group of 8 same-parity sites
+constexpr uint32_t kCodeBias = 0x1000u;             // half a tf32 ulp, in fp32 mantissa units
+__host__ __device__ __forceinline__ int code_groups_per_row(int Qw) { return 2 * ((Qw + 15) >> 4); }
 __host__ __device__ __forceinline__ size_t code_site_offset(size_t row, int Qw, int qw) {
-  const size_t Qw8 = (size_t)((Qw + 7) >> 3);
-  return ((row * Qw8 + (size_t)(qw >> 3)) * 2 + (size_t)(qw & 1)) * kCodeGroup + (size_t)(((qw & 7) >> 1) * 8);
+  return (row * (size_t)code_groups_per_row(Qw) + (size_t)(2 * (qw >> 4) + (qw & 1))) * kCodeGroup + (size_t)(((qw & 15) >> 1) * 4);
 }
-__host__ __device__ __forceinline__ size_t code_floats(size_t rows, int Qw) { return rows * (size_t)((Qw + 7) >> 3) * 8 * kNA; }
+__host__ __device__ __forceinline__ size_t code_floats(size_t rows, int Qw) { return rows * (size_t)code_groups_per_row(Qw) * kCodeGroup; }
+__device__ __forceinline__ float code_enc(float z) { return __uint_as_float(__float_as_uint(z) + kCodeBias); }
+__device__ __forceinline__ float code_dec(float w) { return __uint_as_float(__float_as_uint(w) - kCodeBias); }
 
 struct AnaTcParams {
   Geo g;
-  float* z;             // internal code layout (quad-blocked channels-last, see code_site_offset), updated in place
+  float* z;             // internal code layout (see code_site_offset), pre-biased words, updated in place
   const float* wpack;   // this layer: [2 ranks][49 k-steps][11 groups][2][8][4] tf32-rounded filters
   const float* t0;      // [M]
   const float* t1;      // [M]
@@ -277,38 +289,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
       int qd, qh0, qw0;
       ana_tile_coords(p, tile, n, qd, qh0, qw0);
       const int qh = qh0 + 4 * quad + r4, qw = qw0 + 2 * i8 + (int)rank;
-      valid = qh < g.Qh && qw < g.Qw && !(p.dbg_mode & 2);
-      // this thread's blocks of 8 subbands, 128 B apart; 4 lanes (4 sites of a group) fill each line
-      zs = p.z + code_site_offset(((size_t)n * g.Qd + qd) * g.Qh + qh, g.Qw, qw) + b0 * kCodeBlk;
+      // bit 0: the row exists (loads and stores happen); bit 1: the site exists (else it is layout padding: stored as 0)
+      valid = (qh < g.Qh && !(p.dbg_mode & 2)) ? (1 | (qw < g.Qw ? 2 : 0)) : 0;
+      // this thread's 4-subband chunks, 128 B apart; the 8 lanes of a tile row (one group) fill each 128-byte line
+      zs = p.z + code_site_offset(((size_t)n * g.Qd + qd) * g.Qh + min(qh, g.Qh - 1), g.Qw, qw) + 2 * b0 * kCodeChunk;
     };
-    // ... and ahead of the register loads one bulk L2 prefetch per tile row (16 sites x 704 B contiguous) turns the
-    // DRAM reads into large sequential bursts
+    // ... and ahead of the register loads one bulk L2 prefetch per tile row (the two groups of a 16-site block are
+    // 2 x 5632 B contiguous) turns the DRAM reads into large sequential bursts
     auto prefetch_rows = [&](int tile) {
       if (p.first || part != 0 || i8 != 0 || (r4 & 1) != (int)rank || tile >= p.ntiles) return;
       int n2, qd2, qh02, qw02;
       ana_tile_coords(p, tile, n2, qd2, qh02, qw02);
       const int qh2 = qh02 + 4 * quad + r4;
       if (qh2 >= g.Qh) return;
-      const int nq = (min(kATile, g.Qw - qw02) + 7) & ~7;
-      bulk_prefetch_l2(p.z + code_site_offset(((size_t)n2 * g.Qd + qd2) * g.Qh + qh2, g.Qw, qw02), (uint32_t)nq * kNA * 4);
+      bulk_prefetch_l2(p.z + code_site_offset(((size_t)n2 * g.Qd + qd2) * g.Qh + qh2, g.Qw, qw02), 2u * kCodeGroup * 4);   // both parities' groups
     };
     float zr[8 * kMaxB];
     float* zs; int n, valid;
 #ifndef CDL_ANA_PF
 #define CDL_ANA_PF 2          // bulk L2 prefetch distance in tiles (3+ thrashes L2: measured 4.3 -> 5.1 ms)
 #endif
-#ifndef CDL_ANA_EVICT
-#define CDL_ANA_EVICT 2       // L2 evict-first on the code stores (1) and loads (2): the lines are dead after use
-#endif
 #pragma unroll
     for (int a = 1; a < CDL_ANA_PF; ++a) prefetch_rows(pair + a * npairs);
-#if CDL_ANA_EVICT >= 1
-    const uint64_t pol = l2_policy_evict_first();
-#endif
+    const uint64_t pol = l2_policy_evict_first();                   // code lines are dead after use: evict-first loads and stores
+    auto load_block = [&](const float* base, int b, int ok) {      // 8 subbands = two chunks of 4, pre-biased words
+      ldg128_pred_hint(base + 2 * kCodeChunk * b, *reinterpret_cast<float(*)[4]>(&zr[8 * b]), ok, pol);
+      ldg128_pred_hint(base + 2 * kCodeChunk * b + kCodeChunk, *reinterpret_cast<float(*)[4]>(&zr[8 * b + 4]), ok, pol);
+    };
     if (pair < p.ntiles) {
       site(pair, zs, n, valid);
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) ldg256_pred(zs + kCodeBlk * b, *reinterpret_cast<float(*)[8]>(&zr[8 * b]), valid && !p.first && b < nb);
+      for (int b = 0; b < kMaxB; ++b) load_block(zs, b, (valid & 1) && !p.first && b < nb);
     }
     int it = 0;
     for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
@@ -323,7 +334,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
       prefetch_rows(tile + CDL_ANA_PF * npairs);
       float* zs2 = zs; int n2 = n, valid2 = 0;
       if (tile + npairs < p.ntiles) site(tile + npairs, zs2, n2, valid2);
-      const int ld2 = valid2 && !p.first;
+      const int ld2 = (valid2 & 1) && !p.first;
+      const int st_ok = valid & 1;
+      const uint32_t site_mask = (valid & 2) ? 0xffffffffu : 0u;   // layout padding beyond Qw holds (pre-biased) zeros
       CDL_TW(tw0, mbar_wait(&dfull[ds], (it >> 1) & 1));
       tc_fence_after();
       const uint32_t dcol = lane_addr + kColD + ds * kNA + m0;
@@ -340,18 +353,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
         const float4 t1 = *reinterpret_cast<const float4*>(sTau + m0 + 8 * b + 4);
         const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          zr[8 * b + i] = soft_threshold(__fsub_rn(zr[8 * b + i], __uint_as_float(u[i] ^ usign)), tt[i]);
-#if CDL_ANA_EVICT >= 1
-        stg256_pred_hint(zs + kCodeBlk * b, *reinterpret_cast<const float(*)[8]>(&zr[8 * b]), valid, pol);
-#else
-        stg256_pred(zs + kCodeBlk * b, *reinterpret_cast<const float(*)[8]>(&zr[8 * b]), valid);
-#endif
-#if CDL_ANA_EVICT >= 2
-        ldg256_pred_hint(zs2 + kCodeBlk * b, *reinterpret_cast<float(*)[8]>(&zr[8 * b]), ld2, pol);
-#else
-        ldg256_pred(zs2 + kCodeBlk * b, *reinterpret_cast<float(*)[8]>(&zr[8 * b]), ld2);   // same registers: tile i+1, block b
-#endif
+        for (int i = 0; i < 8; ++i) {
+          const float zin = p.first ? 0.0f : code_dec(zr[8 * b + i]);
+          const float zo = soft_threshold(__fsub_rn(zin, __uint_as_float(u[i] ^ usign)), tt[i]);
+          zr[8 * b + i] = code_enc(__uint_as_float(__float_as_uint(zo) & site_mask));
+        }
+        stg128_pred_hint(zs + 2 * kCodeChunk * b, *reinterpret_cast<const float(*)[4]>(&zr[8 * b]), st_ok, pol);
+        stg128_pred_hint(zs + 2 * kCodeChunk * b + kCodeChunk, *reinterpret_cast<const float(*)[4]>(&zr[8 * b + 4]), st_ok, pol);
+        load_block(zs2, b, ld2);                                 // same registers: tile i+1, block b
         }
       }
       tc_fence_before();                           // accumulator fully read: hand the TMEM slot back to the MMA warp

@@ -169,6 +169,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
                ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
+// cluster-scope release: the arriving thread's prior shared-memory writes are ordered before the arrival for a waiter in
+// another CTA (costs a MEMBAR; used only off the hot path)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -178,8 +184,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// A wait that cannot hang the device: a hand-off that does not arrive within ~2 s traps (the next CUDA call reports a
+// launch failure instead of a hung GPU).  The clock is only read every 1024 failed polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
 }
 // the arrival may come from the peer CTA; same CTA-scope wait (see mbar_arrive_cluster)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
@@ -205,6 +221,18 @@ __device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* m
 __device__ __forceinline__ void tma_load_5d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// The same load issued by either CTA of a cta_group::2 pair, with completion signalled on the mbarrier at the same
+// shared-memory offset in the LEADER CTA (rank 0): the leader's barrier collects the bytes of both CTAs' loads (it
+// expects the sum), so the MMA-issuing warp waits on one local barrier - no relay hop through the peer.
+__device__ __forceinline__ void tma_load_3d_2cta(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("{\n\t.reg .b32 rb;\n\tmapa.shared::cluster.u32 rb, %2, 0;\n\t"
+               "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [rb];\n\t}"
+               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 // one instruction pulls `bytes` (multiple of 16) of contiguous global memory into L2
@@ -261,6 +289,21 @@ __device__ __forceinline__ void ldg256_pred_hint(const float* p, float (&v)[8], 
                "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0; mov.b32 %4, 0; mov.b32 %5, 0; mov.b32 %6, 0; mov.b32 %7, 0;\n\t"
                "@p ld.global.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %10;\n\t}"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p), "r"(ok), "l"(pol));
+}
+// 128-bit (4 x f32) predicated streaming load / store with an L2 policy, 16-byte aligned
+__device__ __forceinline__ void ldg128_pred_hint(const float* p, float (&v)[4], int ok, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+               "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0;\n\t"
+               "@p ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %6;\n\t}"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "r"(ok), "l"(pol));
+}
+__device__ __forceinline__ void stg128_pred_hint(float* p, const float (&v)[4], int ok, uint64_t pol) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p st.global.L2::cache_hint.v4.f32 [%4], {%0,%1,%2,%3}, %6;\n\t}"
+               ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "l"(p), "r"(ok), "l"(pol) : "memory");
+}
+// shared-memory reduction (no return value): concurrent adds from several warps to the same cell do not race
+__device__ __forceinline__ void red_shared_add_f32(float* p, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
 }
 // volatile shared-memory 8-byte load: keeps its place in program order, so a run of them is issued back to back
 __device__ __forceinline__ void lds64(const float* p, float& a, float& b) {

@@ -4,26 +4,29 @@
 //
 // `out` is pre-initialised by the caller with -yp (so that it ends up holding the residual B z - yp) or
 // with 0 (final D z).  Formulation: GEMM + col2im,
-//     Pq[q, t] = sum_m z[q, m] * W[m, t]        M_gemm = 256 coarse sites / CTA pair, K = 176, N = 2 x 176
+//     Pq[q, t] = sum_m z[q, m] * W[m, t]        M_gemm = 2 x 128 coarse sites / CTA pair, K = 176, N = 2 x 176
 //     out[2q - 3 + t] += Pq[q, t]               (overlap-add of each site's 7x7x7 patch)
 //
-//   * cta_group::2, filters resident: each CTA keeps half of the bank (176 taps x 176 subbands, 124 KB).
-//   * Every tcgen05.mma costs >= ~80 cycles whatever its N (measured, profiles/), so the taps are processed in
-//     two passes of N = 176 (25 + 24 rows of 7 taps): 44 MMAs of 88 cycles per tile instead of 132 short ones.
-//     The two accumulators (2 x 176 TMEM columns) double-buffer each other: the col2im of pass p overlaps the
-//     MMAs of the next pass.
-//   * A operand = the code tile: z is kept channels-last (N,Qd,Qh,Qw,176), so a producer thread (one per coarse
-//     site = TMEM lane) reads its subbands with 256-bit loads, rounds to tf32 (RNE - the tensor core truncates)
-//     and tcgen05.st's them into a 2-slot ring of 64 TMEM columns (3 K-chunks per pass; pass 1 re-reads the
-//     tile from L1/L2).
-//   * col2im: taps are ordered (th, td, tw).  A thread first combines its 7 tw-values with its w-neighbours
-//     by warp shuffles (-> the 2 fine voxels of its own cell, plus 5 spill voxels per warp), then adds a
-//     float2 to the CTA's fine tile in shared memory.  Warps (= h-rows of the tile) proceed in lock step
-//     over th (named barrier between th groups), so no two warps ever touch the same row: no shared-memory
-//     atomics.  A CTA pair sweeps consecutive coarse frames of one column, so the footprints of successive tiles
-//     overlap in d inside shared memory (a ring of 9 fine planes): after each tile only the 2 planes that are final
-//     are handed to the producer warps, which add them to `out` with red.global.add.v4.f32 (3.5x fewer global
-//     reductions than flushing every 7-plane footprint) while the col2im warps start the next tile.
+// Round-2 design (the round-1 kernel fed the code through 8 producer warps and a 12-hand-off TMEM ring per tile and
+// drained the accumulators with 4 lock-stepped col2im warps: 36 % tensor-pipe activity):
+//   * NO producer warps.  The code is stored pre-biased in UMMA core-matrix order (cdl_tc_analysis.cuh), so the A
+//     operand goes HBM -> TMA -> shared memory -> tensor core (SS form) without touching a register; the tensor core's
+//     truncation of the pre-biased words IS the round-to-nearest tf32 rounding the parity bar needs.
+//   * A tile = ONE coarse row x 128 sites per CTA (16 groups of 8 sites = 128 TMEM lanes); the two CTAs of a pair
+//     (cta_group::2, M = 256) work on two consecutive tiles and share the resident filter bank (each keeps half: 124 KB).
+//   * Both tap halves (25 + 24 rows of 7 taps, N = 176 each) accumulate in the same K loop, D0 | D1 = 352 TMEM columns:
+//     every 16 KB A chunk (4 K-steps) is read from L2 once and used by 8 MMAs.  44 MMAs per tile issued by one
+//     converged warp (3872 tensor-pipe cycles) from a ring of 3 slots (48 KB in flight), 6 waits + 6 commits per tile;
+//     both CTAs' TMA loads complete on the LEADER's barrier (cta_group::2 form): no relay hop.
+//   * col2im by 16 warps (4 per TMEM lane quadrant, a quarter of the 49 (th,td) rows each).  With a one-row tile every
+//     (th,td) row lands on its own footprint row, so the warps never meet except on the 5 seam columns between
+//     quadrants, which go to a small private spill array merged by the flush: no lock step, no named barriers, no
+//     atomics inside the pass.  The w-direction overlap-add runs on warp shuffles (lane = site, permuted by the group order).
+//   * A CTA sweeps consecutive coarse rows qh of one (n, qd, w-tile) column; the footprints of successive tiles overlap
+//     in h inside a ring of 7 fine rows (x 7 fine frames x 264 columns): after each tile only the 2 rows that became
+//     final are added to `out` (red.global.add.v4.f32) and cleared - by the same 16 warps, while the MMAs of the next
+//     tile run.  The MMA and col2im phases of one accumulator set alternate (352 + 352 columns do not fit TMEM twice).
+//   * Tiles are dealt to the CTAs as equal contiguous ranges of the (column, qh) sequence: perfect balance, long sweeps.
 #pragma once
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
@@ -34,32 +37,49 @@ namespace tc {
 
 constexpr int kKB = 176;                  // GEMM K of the synthesis (subbands, padded) = channels of the code layout
 constexpr int kKBSteps = kKB / 8;         // 22
-constexpr int kNBP = 176;                 // GEMM N per pass
-constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in pass 0 (pass 1: 24)
-constexpr int kColDB = 0, kColAB = 2 * kNBP, kASlotB = 32;   // TMEM: D0 | D1 | A0..A3  (480 of 512)
-constexpr int kASlotsB = 5;               // A ring depth (32 subbands = 4 K-steps per slot; 6 chunks per pass)
-constexpr int kXD = 7, kXH = 13, kXW = 72;                   // fine footprint tile of one CTA (col 0 <-> fine w = 2*qw0 - 4)
-constexpr int kXPlanes = 9;                                  // ring of fine d-planes: 7 being accumulated + 2 being flushed
-constexpr int kXTile = kXPlanes * kXH * kXW;
+constexpr int kNBP = 176;                 // GEMM N per tap half
+constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in half 0 (half 1: 24)
+constexpr int kSTileW = 128;              // coarse sites per tile: one row, 8 blocks of 16 = 16 groups of 8
+constexpr int kSGroups = kSTileW / 8;
+constexpr int kSChunkKS = 4;              // K-steps per A ring slot (the last chunk of a tile holds 2: the TMA box runs past the
+                                          // 176 subbands and is zero-filled there)
+constexpr int kSChunkK4 = 2 * kSChunkKS;  // 4-subband chunks per slot
+constexpr int kSChunkFloats = kSGroups * kSChunkK4 * kCodeChunk;     // 4096 floats = 16 KB
+constexpr int kSChunks = (kKBSteps + kSChunkKS - 1) / kSChunkKS;     // 6 chunks per tile
+constexpr int kSSlots = 3;                // A ring depth: 48 KB in flight.  Every slot is used exactly twice per tile, so slot AND
+                                          // barrier parity of chunk c are compile-time (c % 3, c / 3).  Measured: a wait + commit pair
+                                          // costs the issuing warp ~300 cycles, so it must be amortised over >= 8 MMAs (704 pipe cycles)
+constexpr int kXW = 264;                  // footprint columns: col c <-> fine w = 2*qw0 - 4 + c (cols 1..261 used)
+constexpr int kXPl = 7;                   // fine frames of one coarse frame's footprint
+constexpr int kXRing = 7;                 // ring of fine rows: the 2 rows a tile finishes are flushed (by the same warps) before the
+                                          // next tile's col2im starts, so they are free again for the 2 rows that tile opens
+constexpr int kXTile = kXRing * kXPl * kXW;
+constexpr int kXSpill = kXRing * kXPl * 4 * 8;   // per (ring row, frame, quadrant): 3 left + 2 right seam columns (padded to 8)
+constexpr int kSynC2iWarps = 16;
+constexpr int kSynMmaWarp = 16, kSynLoadWarp = 17;
+constexpr int kSynThreads = 32 * 18;      // 576 (5 warps on two of the four sub-partitions: 96 registers per thread)
+constexpr int kColD0 = 0, kColD1 = kNBP;  // TMEM: D0 | D1 (352 of 512 columns)
 
 struct SynTcParams {
   Geo g;
-  const float* z;       // code in the internal quad-blocked layout (code_site_offset)
+  const float* z;       // code in the internal layout (L2 prefetch only; the operand itself comes through `zmap`)
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
-  const float* wpack;   // this layer: [2 ranks][2 passes][22 k-steps][11 groups][2][8][4]
-  int tiles_w, tiles_h, ntiles;
-  int seg, nseg, nunits; // a CTA pair sweeps `seg` consecutive coarse frames of one (n, h-tile, w-tile) column per unit
-  int a_lo;             // 0: A = rna_tf32(z) ; 1: A = rna_tf32(z - rna_tf32(z))  (low part, used by the 3-term final synthesis)
+  const float* wpack;   // this layer: [2 ranks][2 halves][22 k-steps][11 groups][2][8][4]
+  int tiles_w;          // 128-site tiles per coarse row
+  long long ntiles;     // N * Qd * tiles_w * Qh
+  long long nrows;      // N * Qd * Qh rows of the code tensor (a tile coordinate >= nrows reads zeros)
   long long* dbg;
-  int dbg_mode;         // development aid (results invalid): 512 = producers skip the code loads, 1024 = no L2 prefetch
+  int dbg_mode;         // development aid (results invalid): 64 = col2im skipped, 128 = flush skipped, 256 = no TMA data movement
 };
 
 constexpr size_t kSynSmemB = (size_t)2 * kKBSteps * (kNBP / 2) * 8 * sizeof(float);             // 123904
-constexpr size_t kSynSmemX = (size_t)kXTile * sizeof(float);                                    // 9-plane footprint ring, 33696
-constexpr size_t kSynSmemBytes = kSynSmemB + kSynSmemX + 256;
+constexpr size_t kSynSmemX = ((size_t)kXTile * sizeof(float) + 127) / 128 * 128;                // 51840
+constexpr size_t kSynSmemA = (size_t)kSSlots * kSChunkFloats * sizeof(float);                   // 49152
+constexpr size_t kSynSmemS = (size_t)kXSpill * sizeof(float);                                   // 6272
+constexpr size_t kSynSmemBytes = kSynSmemB + kSynSmemX + kSynSmemA + kSynSmemS + 512;   // + 48 mbarriers, TMEM slot
 
-// filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[pass][n = 7*row + tw, k = m], per-rank UMMA layout, tf32 RNE.
-// Pass 0 holds rows 0..24, pass 1 rows 25..48 of the (th,td) row list (th-major); unused columns are zero.
+// filters (M,1,7,7,7) [index (m, td, th, tw)] -> B[half][n = 7*row + tw, k = m], per-rank UMMA layout, tf32 RNE.
+// Half 0 holds rows 0..24, half 1 rows 25..48 of the (th,td) row list (th-major); unused columns are zero.
 __global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restrict__ out, int M, int lo) {
   const int per_rank = 2 * kKBSteps * (kNBP / 2) * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += gridDim.x * blockDim.x) {
@@ -70,7 +90,7 @@ __global__ void k_pack_tc_synthesis(const float* __restrict__ w, float* __restri
     const int ks = rem / ((kNBP / 2) * 8);
     rem %= (kNBP / 2) * 8;
     const int grp = rem / 64, kc = (rem / 32) % 2, r8 = (rem / 4) % 8, e = rem % 4;
-    const int j = rank * (kNBP / 2) + grp * 8 + r8;            // column inside the pass accumulator
+    const int j = rank * (kNBP / 2) + grp * 8 + r8;            // column inside the half's accumulator
     const int m = ks * 8 + kc * 4 + e;
     const int row = pass * kRowsP0 + j / 7, tw = j % 7;
     float v = 0.0f;
@@ -91,150 +111,143 @@ __global__ void __launch_bounds__(256) k_neg_copy(const float* __restrict__ yp, 
   }
 }
 
-struct EdgeMasks { float lt31, lt30, gt0; };   // 1.0 / 0.0 lane masks: fma(x, mask, acc) adds x only where the neighbour exists
+// ---- tile sequence ----
+struct SynTile { long long row; int n, qd, qh, qw0, valid, first, last; };
+// Tiles are numbered column by column ((n, qd, w-tile), w-tile fastest), qh fastest inside a column.  CTA `cta` of
+// `nctas` owns the contiguous range [cta*T/nctas, (cta+1)*T/nctas); a RUN is a maximal stretch of consecutive qh of one
+// column inside that range (the footprint ring carries over inside a run and is flushed completely at its end).
+__device__ __forceinline__ void syn_range(const SynTcParams& p, int cta, int nctas, long long& t0, long long& t1) {
+  t0 = p.ntiles * cta / nctas;
+  t1 = p.ntiles * (cta + 1) / nctas;
+}
+__device__ __forceinline__ SynTile syn_tile(const SynTcParams& p, long long t0, long long t1, int i) {
+  SynTile t;
+  const long long tau = t0 + i;
+  t.valid = tau < t1;
+  if (!t.valid) { t.row = p.nrows; t.n = t.qd = t.qh = t.qw0 = 0; t.first = t.last = 0; return t; }
+  long long col = tau / p.g.Qh;
+  t.qh = (int)(tau - col * p.g.Qh);
+  t.qw0 = (int)(col % p.tiles_w) * kSTileW; col /= p.tiles_w;
+  t.qd = (int)(col % p.g.Qd);
+  t.n = (int)(col / p.g.Qd);
+  t.row = ((long long)t.n * p.g.Qd + t.qd) * p.g.Qh + t.qh;
+  t.first = (tau == t0) || t.qh == 0;
+  t.last = (tau == t1 - 1) || t.qh == p.g.Qh - 1;
+  return t;
+}
 
-// NR consecutive (th,td) rows R0..R0+NR-1, all inside one th group, whose taps sit in u[7*(R-RC0) .. +6].
-// Phase 1: w-direction reduction with shuffles (independent across rows), phase 2: all shared-memory loads,
-// phase 3: adds and stores - so the NR read-modify-writes overlap instead of forming one dependent chain.
-template <int R0, int NR, int RC0, int COLS>
-__device__ __forceinline__ void rows_apply(const uint32_t (&u)[COLS], float* xs, int pbase, int hrow, int lane, const EdgeMasks& em) {
-  constexpr int th = R0 / 7;
+// ---- col2im of NR consecutive (th,td) rows whose taps sit in u[7*i .. 7*i+6] ----
+// lane = site (permuted); x0 / x1 = the two fine voxels of the site's own cell after the w-direction overlap-add:
+//   fine 2o   : taps 3 (own), 1 (o+1), 5 (o-1)          fine 2o+1 : taps 4 (own), 2 (o+1), 0 (o+2), 6 (o-1)
+// A quadrant's 64 own columns are touched by its warps only.  What spills over the quadrant's ends (fine -3..-1 from
+// site 0, fine 64, 65 from site 31) belongs to columns another quadrant's warps own: it goes to a small private spill
+// array instead (per ring row, frame and quadrant) and is merged by the flush - plain read-modify-writes everywhere
+// (fp32 shared-memory atomics are CAS loops on this architecture: measured 1.7x slower than the round-1 kernel).
+struct C2iLane { int src1, src2, srcm; float m1, m2, mm; int o; };
+
+template <int ROW0, int NR>
+__device__ __forceinline__ void c2i_rows(const uint32_t (&u)[7 * NR], float* xs, float* ss, int pbase, int colbase, int q, const C2iLane& L) {
   const unsigned full = 0xffffffffu;
-  float x0[NR], x1[NR], e1[NR], e2[NR], e3[NR], f5[NR], f6[NR];
+  float x0[NR], x1[NR], e3[NR];
+  int cell[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
-    const int o = 7 * (R0 + i - RC0);
-    const float v0 = __uint_as_float(u[o]), v1 = __uint_as_float(u[o + 1]), v2 = __uint_as_float(u[o + 2]),
-                v3 = __uint_as_float(u[o + 3]), v4 = __uint_as_float(u[o + 4]), v5 = __uint_as_float(u[o + 5]),
-                v6 = __uint_as_float(u[o + 6]);
-    const float a1 = __shfl_down_sync(full, v1, 1), a2 = __shfl_down_sync(full, v2, 1), a0 = __shfl_down_sync(full, v0, 2);
-    const float b5 = __shfl_up_sync(full, v5, 1), b6 = __shfl_up_sync(full, v6, 1);
-    const float n0 = __shfl_down_sync(full, v0, 1);            // lane 1's v0, used by lane 0 (spill to fine -1)
-    x0[i] = fmaf(b5, em.gt0, fmaf(a1, em.lt31, v3));           // fine w = 2q   : taps 3 (own), 1 (q+1), 5 (q-1)
-    x1[i] = fmaf(b6, em.gt0, fmaf(a0, em.lt30, fmaf(a2, em.lt31, v4)));   // fine w = 2q+1 : taps 4, 2 (q+1), 0 (q+2), 6 (q-1)
-    e1[i] = v0; e2[i] = v1; e3[i] = v2 + n0; f5[i] = v5; f6[i] = v6;
+    const int row = ROW0 + i, th = row / 7, td = row % 7;
+    const float v0 = __uint_as_float(u[7 * i]), v1 = __uint_as_float(u[7 * i + 1]), v2 = __uint_as_float(u[7 * i + 2]),
+                v3 = __uint_as_float(u[7 * i + 3]), v4 = __uint_as_float(u[7 * i + 4]), v5 = __uint_as_float(u[7 * i + 5]),
+                v6 = __uint_as_float(u[7 * i + 6]);
+    const float a1 = __shfl_sync(full, v1, L.src1), a2 = __shfl_sync(full, v2, L.src1), n0 = __shfl_sync(full, v0, L.src1);
+    const float a0 = __shfl_sync(full, v0, L.src2);
+    const float b5 = __shfl_sync(full, v5, L.srcm), b6 = __shfl_sync(full, v6, L.srcm);
+    x0[i] = fmaf(b5, L.mm, fmaf(a1, L.m1, v3));
+    x1[i] = fmaf(b6, L.mm, fmaf(a0, L.m2, fmaf(a2, L.m1, v4)));
+    e3[i] = v2 + n0;
+    int ps = pbase + th; if (ps >= kXRing) ps -= kXRing;          // ring slot of fine row 2*qh + th
+    cell[i] = ps * kXPl + td;
   }
-  float* rowp[NR];
   float2 cur[NR];
 #pragma unroll
-  for (int i = 0; i < NR; ++i) {
-    const int td = (R0 + i) % 7;
-    const int ps = pbase + td - ((pbase + td >= kXPlanes) ? kXPlanes : 0);          // ring slot of fine plane 2*qd + td
-    rowp[i] = xs + (ps * kXH + 2 * hrow + th) * kXW;
-    cur[i] = *reinterpret_cast<const float2*>(rowp[i] + 4 + 2 * lane);
-  }
+  for (int i = 0; i < NR; ++i) cur[i] = *reinterpret_cast<const float2*>(xs + cell[i] * kXW + colbase);
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     cur[i].x += x0[i]; cur[i].y += x1[i];
-    *reinterpret_cast<float2*>(rowp[i] + 4 + 2 * lane) = cur[i];
+    *reinterpret_cast<float2*>(xs + cell[i] * kXW + colbase) = cur[i];
   }
-  // Spill voxels outside the warp's 64 own columns: lane 0 holds the left three (fine w = 2*qw0 - 3 .. -1 = tile
-  // columns 1..3), lane 31 the right two (2*qw0 + 64, 65 = tile columns 68, 69).  One float4 read-modify-write at a
-  // lane-dependent address serves both in a single divergent region (two lanes active) instead of two.
-  if (lane == 0 || lane == 31) {
-    const int off = lane ? 68 : 0;
-    float4 q[NR];
+  if (L.o == 0 || L.o == 31) {                                     // one divergent region, two lanes: the seam columns
+    const int off = L.o ? 4 : 0;                                   // [0..2] left spill (fine -3,-2,-1), [4..5] right spill (fine 64, 65)
+    float4 sp[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] = *reinterpret_cast<const float4*>(rowp[i] + off);
+    for (int i = 0; i < NR; ++i) sp[i] = *reinterpret_cast<const float4*>(ss + (cell[i] * 4 + q) * 8 + off);
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      q[i].x += lane ? f5[i] : 0.0f; q[i].y += lane ? f6[i] : e1[i];
-      q[i].z += lane ? 0.0f : e2[i]; q[i].w += lane ? 0.0f : e3[i];
-      *reinterpret_cast<float4*>(rowp[i] + off) = q[i];
+      sp[i].x += L.o ? __uint_as_float(u[7 * i + 5]) : __uint_as_float(u[7 * i]);
+      sp[i].y += L.o ? __uint_as_float(u[7 * i + 6]) : __uint_as_float(u[7 * i + 1]);
+      sp[i].z += L.o ? 0.0f : e3[i];
+      *reinterpret_cast<float4*>(ss + (cell[i] * 4 + q) * 8 + off) = sp[i];
     }
   }
 }
 
-// rows [R, REND) whose first row RC0 sits at u[0], split at th-group boundaries; warps run the th groups in lock
-// step (named barrier 2) so that no two warps ever touch the same shared-memory row at the same time
-template <int R, int REND, int RC0, int COLS>
-__device__ __forceinline__ void rows_walk(const uint32_t (&u)[COLS], float* xs, int pbase, int hrow, int lane, const EdgeMasks& em) {
-  if constexpr (R < REND) {
-    constexpr int RB = ((R / 7) + 1) * 7 < REND ? ((R / 7) + 1) * 7 : REND;
-    if constexpr (R % 7 == 0 && R > 0) ptx::named_bar_sync(2, 128);
-    rows_apply<R, RB - R, RC0, COLS>(u, xs, pbase, hrow, lane, em);
-    rows_walk<RB, REND, RC0, COLS>(u, xs, pbase, hrow, lane, em);
-  }
-}
-
-struct SynTile { int n, qd, qh0, qw0, first, last; };
-// j-th tile of CTA pair `pair`: unit u = pair + (j / seg) * npairs is a (n, d-segment, h-tile, w-tile) column of `seg`
-// consecutive coarse frames, swept in order of qd
-__device__ __forceinline__ SynTile syn_tile(const SynTcParams& p, int pair, int npairs, int j) {
-  int u = pair + (j / p.seg) * npairs;
-  const int k = j % p.seg;
-  SynTile t;
-  t.qw0 = (u % p.tiles_w) * kTW; u /= p.tiles_w;
-  t.qh0 = (u % p.tiles_h) * 2 * kTH; u /= p.tiles_h;
-  t.qd = (u % p.nseg) * p.seg + k;
-  t.n = u / p.nseg;
-  t.first = k == 0; t.last = k == p.seg - 1;
-  return t;
-}
-
-// one accumulator pass (176 columns = rows [RFIRST, RLAST) of 7 taps) drained in three 64-column loads of 9/9/rest rows
-template <int RFIRST, int RLAST>
-__device__ __forceinline__ void syn_epilogue_pass(uint32_t dcol, float* xs, int pbase, int hrow, int lane, const EdgeMasks& em,
-                                                  uint64_t* dempty_p, uint64_t* dfull_p, uint32_t parity, long long& tw, uint32_t rank) {
+// rows [ROW0, ROW0 + NROWS) of the (th,td) row list, accumulator columns starting at `acol` (row ROW0's tap 0), drained
+// four rows (one 32-column tcgen05.ld) at a time; the next load is in flight while the current rows are applied
+// `released`: called once the last tcgen05.ld of the part has completed (the accumulator can go back to the MMA warp
+// while the last rows are still being applied)
+template <int ROW0, int NROWS, int DONE = 0, typename Rel>
+__device__ __forceinline__ void c2i_part(uint32_t acol, uint32_t (&u)[32], float* xs, float* ss, int pbase, int colbase, int q, const C2iLane& L,
+                                         Rel released) {
   using namespace ptx;
-  CDL_TW(tw, mbar_wait(dfull_p, parity));
-  tc_fence_after();
-  {
-    uint32_t u[64];
-    tmem_ld64(dcol, u);
-    tmem_wait_ld();
-    rows_walk<RFIRST, RFIRST + 9, RFIRST, 64>(u, xs, pbase, hrow, lane, em);
-  }
-  {
-    uint32_t u[64];
-    tmem_ld64(dcol + 63, u);
-    tmem_wait_ld();
-    rows_walk<RFIRST + 9, RFIRST + 18, RFIRST + 9, 64>(u, xs, pbase, hrow, lane, em);
-  }
-  {
-    uint32_t u[64];
-    tmem_ld64(dcol + 126, u);                      // rows RFIRST+18 .. RLAST-1 (49 or 42 columns); the rest is ignored
-    tmem_wait_ld();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) { if (rank == 0) mbar_arrive(dempty_p); else mbar_arrive_cluster(dempty_p, 0); }   // accumulator free again
-    rows_walk<RFIRST + 18, RLAST, RFIRST + 18, 64>(u, xs, pbase, hrow, lane, em);
-  }
+  if constexpr (DONE == 0) tmem_ld32(acol, u);
+  constexpr int NR = (NROWS - DONE) < 4 ? (NROWS - DONE) : 4;
+  tmem_wait_ld();
+  uint32_t v[7 * NR];
+#pragma unroll
+  for (int i = 0; i < 7 * NR; ++i) v[i] = u[i];
+  if constexpr (DONE + NR < NROWS) tmem_ld32(acol + 7 * (DONE + NR), u);
+  else released();
+  c2i_rows<ROW0 + DONE, NR>(v, xs, ss, pbase, colbase, q, L);
+  if constexpr (DONE + NR < NROWS) c2i_part<ROW0, NROWS, DONE + NR>(acol, u, xs, ss, pbase, colbase, q, L, released);
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_synthesis(const SynTcParams p) {
+// LO = false: A = rna_tf32(z) (what the tensor core reads from the pre-biased words)
+// LO = true : A = rna_tf32(z - rna_tf32(z)), formed in shared memory by the (then idle) col2im warps - the low part used
+//             by the 3-term final dictionary synthesis
+template <bool LO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc_synthesis(const SynTcParams p, const __grid_constant__ CUtensorMap zmap) {
   using namespace ptx;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* sB = reinterpret_cast<float*>(smem_raw);
   float* sX = reinterpret_cast<float*>(smem_raw + kSynSmemB);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kSynSmemB + kSynSmemX);
+  float* sA = reinterpret_cast<float*>(smem_raw + kSynSmemB + kSynSmemX);
+  float* sS = reinterpret_cast<float*>(smem_raw + kSynSmemB + kSynSmemX + kSynSmemA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kSynSmemB + kSynSmemX + kSynSmemA + kSynSmemS);
   uint64_t* wbar = bars + 0;
-  uint64_t* afull = bars + 1;                  // [kASlotsB] (leader) producers of both CTAs -> MMA
-  uint64_t* aempty = afull + kASlotsB;         // [kASlotsB] MMA commit (multicast) -> producers
-  uint64_t* dfull = aempty + kASlotsB;         // [2] MMA commit (multicast) -> epilogue   (index = pass)
-  uint64_t* dempty = dfull + 2;                // [2] (leader) epilogue warps of both CTAs -> MMA
-  uint64_t* wready = dempty + 2;               //     (leader) the peer CTA's filters have landed
-  uint64_t* xfull = wready + 1;                // [2] epilogue -> producers: footprint planes complete, flush them
-  uint64_t* xfree = xfull + 2;                 // [2] producers -> epilogue: planes flushed and cleared
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfree + 2);
+  uint64_t* wready = bars + 1;                 //      (leader) the peer CTA's filters have landed
+  uint64_t* afull = bars + 2;                  // [3]  TMA: (leader) BOTH CTAs' A chunks landed -> MMA;  LO: this CTA's chunk landed
+  uint64_t* aboth = afull + kSSlots;           // [3]  LO only: (leader) chunk transformed in place by the col2im warps of both CTAs -> MMA
+  uint64_t* aempty = aboth + kSSlots;          // [3]  MMA commit (multicast) -> TMA warps
+  uint64_t* dfull = aempty + kSSlots;          //      MMA commit (multicast) -> col2im of both CTAs
+  uint64_t* dempty = dfull + 1;                //      (leader) col2im warps of both CTAs -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 1);
 
   const Geo& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0, tw5 = 0;
+  long long tw0 = 0, tw1 = 0, tw2 = 0;
   const long long tstart = clock64();
 
   if (tid == 0) {
     mbar_init(wbar, 1);
     mbar_init(wready, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 4); mbar_init(&xfree[i], 8); }
-    for (int i = 0; i < kASlotsB; ++i) { mbar_init(&afull[i], 16); mbar_init(&aempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 8); }
+    for (int i = 0; i < kSSlots; ++i) {
+      mbar_init(&afull[i], 1); mbar_init(&aboth[i], 2 * kSynC2iWarps); mbar_init(&aempty[i], 1);
+    }
+    mbar_init(dfull, 1);
+    mbar_init(dempty, 2 * kSynC2iWarps);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
-  for (int i = tid; i < kXTile; i += kThreads) sX[i] = 0.0f;
+  if (warp == kSynMmaWarp) { tmem_alloc<2>(tmem_slot, 512); tmem_relinquish<2>(); }
+  for (int i = tid; i < kXTile; i += kSynThreads) sX[i] = 0.0f;
+  for (int i = tid; i < kXSpill; i += kSynThreads) sS[i] = 0.0f;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(wbar, (uint32_t)kSynSmemB);
@@ -246,156 +259,170 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   cluster_sync_all();          // barriers initialised, TMEM allocated (filters may still be in flight)
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
-  const int my_tiles = (pair < p.nunits) ? ((p.nunits - pair + npairs - 1) / npairs) * p.seg : 0;
 
-  if (warp < 8) {
-    // ============================== producers: code tile -> tf32 -> TMEM A ring; footprint flush ==============================
-    // warp = 4*half + quad: TMEM lanes of tile row `quad`; `half` selects which half of every K-chunk this warp converts
-    const int quad = warp & 3, half = warp >> 2;
-    const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
-    // After tile j (coarse frame qd) the fine planes 2*qd-od and 2*qd-od+1 are final (all 7 of the footprint at the end
-    // of a unit): out[fine] += plane, then clear its ring slot.
-    auto flush_tile = [&](int j) {
-      const SynTile t = syn_tile(p, pair, npairs, j);
-      CDL_TW(tw1, mbar_wait(&xfull[j & 1], (j >> 1) & 1));
-      const int fh0 = 2 * (t.qh0 + (int)rank * kTH) - 3, fw0 = 2 * t.qw0 - 4;
-      float* on = p.out + (size_t)t.n * g.fine_vol();
-      const int nrows = (t.last ? kXD : 2) * kXH;
-      for (int r = warp; r < nrows; r += 8) {                    // one 72-float row per warp pass, 18 float4 per row
-        const int h = r % kXH, pi = r / kXH;
-        const int pr = 2 * t.qd + pi;                            // plane index along the sweep; fine d = pr - od
-        const int gd = pr - g.od, gh = fh0 + h, gw = fw0 + 4 * lane;
-        if (lane < kXW / 4) {
-          float4* cell = reinterpret_cast<float4*>(sX + ((pr % kXPlanes) * kXH + h) * kXW + 4 * lane);
-          const float4 v = *cell;
+  // this CTA's tile range and the pair's common number of rounds
+  long long t0, t1, pt0, pt1;
+  syn_range(p, blockIdx.x, gridDim.x, t0, t1);
+  syn_range(p, blockIdx.x ^ 1, gridDim.x, pt0, pt1);
+  const int mylen = (int)(t1 - t0);
+  const int rounds = max(mylen, (int)(pt1 - pt0));
+
+  if (warp < kSynC2iWarps) {
+    // ============================== col2im + footprint flush ==============================
+    const int q = warp & 3, part = warp >> 2;
+    const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+    // lane -> site: TMEM lane 8*g' + i of the quadrant is row i of group g' = site 16*(g'>>1) + 2*i + (g'&1)
+    C2iLane L;
+    {
+      const int gq = lane >> 3, i8 = lane & 7;
+      L.o = 16 * (gq >> 1) + 2 * i8 + (gq & 1);
+      auto lane_of = [](int o) { o &= 31; return 8 * (2 * (o >> 4) + (o & 1)) + ((o & 15) >> 1); };
+      L.src1 = lane_of(L.o + 1); L.src2 = lane_of(L.o + 2); L.srcm = lane_of(L.o + 31);
+      L.m1 = L.o < 31 ? 1.0f : 0.0f; L.m2 = L.o < 30 ? 1.0f : 0.0f; L.mm = L.o > 0 ? 1.0f : 0.0f;
+    }
+    const int colbase = 4 + 64 * q + 2 * L.o;
+    for (int it = 0; it < rounds; ++it) {
+      const SynTile t = syn_tile(p, t0, t1, it);
+      if (LO) {
+        // low part of the code, in place: word -> z = word - bias, hi = truncate(word) = rna(z), word' = (z - hi) + bias
+#pragma unroll 1
+        for (int c = 0; c < kSChunks; ++c) {
+          const int slot = c % kSSlots;
+          mbar_wait(&afull[slot], c / kSSlots);
+          auto lo_word = [](float x) {
+            const uint32_t b = __float_as_uint(x);
+            if (b == 0u) return 0.0f;                                                   // TMA zero fill (no site): stays zero
+            const float z = __uint_as_float(b - kCodeBias), hi = __uint_as_float(b & 0xffffe000u);
+            return __uint_as_float(__float_as_uint(z - hi) + kCodeBias);
+          };
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {                                                 // 512 threads x 2 x 16 B = one chunk
+            float4* pa = reinterpret_cast<float4*>(sA + slot * kSChunkFloats) + h * 32 * kSynC2iWarps + tid;
+            float4 w = *pa;
+            w.x = lo_word(w.x); w.y = lo_word(w.y); w.z = lo_word(w.z); w.w = lo_word(w.w);
+            *pa = w;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_release(&aboth[slot], 0);                // 32 warps of the pair -> the leader's MMA warp
+        }
+      }
+      CDL_TW(tw0, mbar_wait(dfull, it & 1));
+      tc_fence_after();
+      const int pbase = (2 * t.qh) % kXRing;
+      auto release = [&]() {                                       // this warp's columns are in registers: accumulators free again
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (rank == 0) mbar_arrive(dempty); else mbar_arrive_cluster(dempty, 0); }
+      };
+      if (t.valid && !(p.dbg_mode & 64)) {
+        uint32_t u[32];
+        switch (part) {                                            // warp-uniform: a quarter of the 49 rows each
+          case 0: c2i_part<0, 13>(lane_addr + kColD0, u, sX, sS, pbase, colbase, q, L, release); break;
+          case 1: c2i_part<13, 12>(lane_addr + kColD0 + 7 * 13, u, sX, sS, pbase, colbase, q, L, release); break;
+          case 2: c2i_part<25, 12>(lane_addr + kColD1, u, sX, sS, pbase, colbase, q, L, release); break;
+          default: c2i_part<37, 12>(lane_addr + kColD1 + 7 * 12, u, sX, sS, pbase, colbase, q, L, release); break;
+        }
+      } else {
+        release();
+      }
+      named_bar_sync(1, 32 * kSynC2iWarps);                        // every warp's rows are in the ring
+      if (t.valid && !(p.dbg_mode & 128)) {
+        // fine rows 2*qh and 2*qh+1 are final (all 7 at the end of a run): out += row, clear the ring slot.  Runs while
+        // the MMAs of the next tile are in flight.
+        const int nfl = t.last ? kXPl : 2;
+        const int items = nfl * kXPl * (kXW / 4);
+        float* on = p.out + (size_t)t.n * g.fine_vol();
+        const int gw0 = 2 * t.qw0 - 4;
+        for (int item = tid; item < items; item += 32 * kSynC2iWarps) {
+          const int c4 = item % (kXW / 4), rest = item / (kXW / 4);
+          const int td = rest % kXPl, pi = rest / kXPl;
+          const int pr = 2 * t.qh + pi;                            // fine row along the sweep; fine h = pr - oh
+          const int gd = 2 * t.qd + td - g.od, gh = pr - g.oh, gw = gw0 + 4 * c4;
+          const int rc = (pr % kXRing) * kXPl + td;
+          float4* cell = reinterpret_cast<float4*>(sX + rc * kXW + 4 * c4);
+          float4 v = *cell;
           *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+          // the seam columns: quadrant qq's left spill lands on columns 64 qq + 1..3, its right spill on 64 qq + 68, 69
+          if ((c4 & 15) == 0 && c4 < 64) {
+            float4* sp = reinterpret_cast<float4*>(sS + (rc * 4 + (c4 >> 4)) * 8);
+            const float4 l = *sp;
+            *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+            v.y += l.x; v.z += l.y; v.w += l.z;
+          } else if ((c4 & 15) == 1 && c4 >= 17) {
+            float4* sp = reinterpret_cast<float4*>(sS + (rc * 4 + ((c4 - 17) >> 4)) * 8 + 4);
+            const float4 r = *sp;
+            *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x += r.x; v.y += r.y;
+          }
           if (gd >= 0 && gd < g.Fd && gh >= 0 && gh < g.Fh && gw >= 0 && gw + 4 <= g.Fw)
             red_add_v4_f32(on + ((size_t)gd * g.Fh + gh) * g.Fw + gw, v);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xfree[j & 1]);
-    };
-    const int a_lo = p.a_lo;
-    auto cvt_a = [a_lo](float x) {
-      const float hi = __uint_as_float(tf32_rna_bits(x));
-      return a_lo ? __uint_as_float(tf32_rna_bits(x - hi)) : hi;
-    };
-    int it = 0;
-    uint32_t gch = 0;
-    float rg[6][16];
-    for (; it < my_tiles; ++it) {
-      const SynTile t = syn_tile(p, pair, npairs, it);
-      const SynTile t2 = syn_tile(p, pair, npairs, it + 1 < my_tiles ? it + 1 : it);
-      const int qh = t.qh0 + rank * kTH + quad, qw = t.qw0 + lane;
-      const int valid = qh < g.Qh && qw < g.Qw && !(p.dbg_mode & 512);
-      const float* zs = p.z + code_site_offset(((size_t)t.n * g.Qd + t.qd) * g.Qh + qh, g.Qw, qw);
-      // bulk L2 prefetch two tiles ahead (the register refill below already requests tile it+1 during tile it): one
-      // contiguous 22.5 KB burst per tile row keeps the DRAM reads sequential
-      if (half == 0 && lane == 0) {
-        for (int a = 1; a <= 1; ++a) {
-          if (it + a >= my_tiles) break;
-          const SynTile t3 = syn_tile(p, pair, npairs, it + a);
-          const int qh3 = t3.qh0 + rank * kTH + quad;
-          if (qh3 < g.Qh) {
-            const int nq = (min(kTW, g.Qw - t3.qw0) + 7) & ~7;
-            bulk_prefetch_l2(p.z + code_site_offset(((size_t)t3.n * g.Qd + t3.qd) * g.Qh + qh3, g.Qw, t3.qw0), (uint32_t)nq * kKB * 4);
-          }
-        }
-      }
-      // This thread's 88 subbands (its half of the six 32-subband K-chunks: 5 x 16 + 8) live in registers for the whole
-      // tile: converted to tf32 once, stored to TMEM in both passes.  Right after a group's pass-1 store its registers
-      // are reloaded with the NEXT tile's values, so every load has several chunk periods to land.
-      auto load_group = [&](float (&dst)[16], const float* base, int c, int ok) {
-        if (c < 5) {                                             // subbands 32c + 16*half + [0,16) = blocks 4c + 2*half, +1
-          ldg256_pred(base + (4 * c + 2 * half) * kCodeBlk, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
-          ldg256_pred(base + (4 * c + 2 * half + 1) * kCodeBlk, *reinterpret_cast<float(*)[8]>(&dst[8]), ok);
-        } else {                                                 // subbands 160 + 8*half + [0,8) = block 20 + half
-          ldg256_pred(base + (20 + half) * kCodeBlk, *reinterpret_cast<float(*)[8]>(&dst[0]), ok);
-        }
-      };
-      if (it == 0) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) load_group(rg[c], zs, c, valid);
-      }
-      const float* zs2 = zs;                                     // the next tile's site (for the register refill)
-      int valid2 = 0;
-      if (it + 1 < my_tiles) {
-        const int qh2 = t2.qh0 + rank * kTH + quad, qw2 = t2.qw0 + lane;
-        valid2 = qh2 < g.Qh && qw2 < g.Qw && !(p.dbg_mode & 512);
-        zs2 = p.z + code_site_offset(((size_t)t2.n * g.Qd + t2.qd) * g.Qh + qh2, g.Qw, qw2);
-      }
-#pragma unroll
-      for (int pc = 0; pc < 12; ++pc, ++gch) {                   // 2 passes x 6 K-chunks of 32 subbands (the last holds 16)
-        const int c = pc % 6;
-        const uint32_t slot = gch % kASlotsB;
-        const uint32_t acol = lane_addr + kColAB + slot * kASlotB;
-        if (pc < 6) {                                            // first use of the group: round to tf32 in place
-#pragma unroll
-          for (int i = 0; i < 16; ++i) rg[c][i] = cvt_a(rg[c][i]);
-        }
-        CDL_TW(tw0, mbar_wait(&aempty[slot], ((gch / kASlotsB) & 1) ^ 1));
-        tc_fence_after();
-        if (c < 5) tmem_st16(acol + 16 * half, *reinterpret_cast<const uint32_t(*)[16]>(&rg[c][0]));
-        else tmem_st8(acol + 8 * half, *reinterpret_cast<const uint32_t(*)[8]>(&rg[c][0]));
-        CDL_TW(tw4, tmem_wait_st(); tc_fence_before(); __syncwarp(); if (lane == 0) { if (rank == 0) mbar_arrive(&afull[slot]); else mbar_arrive_cluster(&afull[slot], 0); });
-        if (pc >= 6) load_group(rg[c], zs2, c, valid2);          // group is dead for this tile: refill it for the next one
-      }
-      CDL_TW(tw5, if (it > 0) flush_tile(it - 1));
+      named_bar_sync(1, 32 * kSynC2iWarps);   // the flushed rows are clear before the next tile's col2im reuses their ring slots
     }
-    if (it > 0) flush_tile(it - 1);                                // planes of the last tile
-  } else if (warp < kMmaWarp) {
-    // ============================== epilogue: col2im ==============================
-    const int ew = warp - 8;
-    const uint32_t lane_addr = tbase + ((uint32_t)(ew * 32) << 16);
-    const EdgeMasks em = {lane < 31 ? 1.0f : 0.0f, lane < 30 ? 1.0f : 0.0f, lane > 0 ? 1.0f : 0.0f};
-    for (int it = 0; it < my_tiles; ++it) {
-      const SynTile t = syn_tile(p, pair, npairs, it);
-      const int xb = it & 1;
-      // the two planes this tile opens (2*qd+5, 2*qd+6) reuse the ring slots flushed after tile it-2 ...
-      CDL_TW(tw1, mbar_wait(&xfree[xb], ((it >> 1) & 1) ^ 1));
-      // ... and a new unit may start anywhere in the ring: wait for the complete flush that ended the previous unit
-      if (t.first && it > 0) CDL_TW(tw1, mbar_wait(&xfree[(it - 1) & 1], ((it - 1) >> 1) & 1));
-      const int pbase = (2 * t.qd) % kXPlanes;
-      syn_epilogue_pass<0, kRowsP0>(lane_addr + kColDB, sX, pbase, ew, lane, em, &dempty[0], &dfull[0], it & 1, tw0, rank);
-      syn_epilogue_pass<kRowsP0, 49>(lane_addr + kColDB + kNBP, sX, pbase, ew, lane, em, &dempty[1], &dfull[1], it & 1, tw0, rank);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&xfull[xb]);      // this warp's rows are in; 4 arrivals -> producers flush the final planes
-      named_bar_sync(2, 128);                      // th lock step restarts with everyone at group 0
-    }
-  } else {
-    // ============================== MMA issue (leader CTA, one thread) ==============================
-    // (the warp-converged issue form of the analysis kernel measured SLOWER here: this kernel is bound by its col2im
-    // warps, and a faster-spinning MMA warp only takes issue slots from the col2im warp it shares a scheduler with)
+  } else if (warp == kSynMmaWarp) {
+    // ============================== MMA issue (leader CTA; converged warp, elected lane) ==============================
     if (rank == 1 && lane == 0) { mbar_wait(wbar, 0); mbar_arrive_cluster(wready, 0); }
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       CDL_TW(tw2, mbar_wait(wbar, 0); mbar_wait_cluster(wready, 0));
-      const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
-      constexpr uint32_t kBStep = ((kNBP / 2) * 32) >> 4;           // 16-byte units between k-steps of B (88 rows x 32 B)
       const uint32_t idesc = make_idesc_tf32(256, kNBP);
-      int it = 0;
-      uint32_t gch = 0;
-      for (; it < my_tiles; ++it) {
-        for (int pass = 0; pass < 2; ++pass) {
-          CDL_TW(tw0, mbar_wait_cluster(&dempty[pass], (it & 1) ^ 1));
+      const uint64_t bdesc0 = make_smem_desc_kmajor_noswz(smem_u32(sB), 128, 256);
+      const uint64_t adesc0 = make_smem_desc_kmajor_noswz(smem_u32(sA), 128, kSChunkK4 * 128);
+      constexpr uint32_t kBStep = ((kNBP / 2) * 32) >> 4;           // 16-byte units between k-steps of B (88 rows x 32 B)
+      for (int it = 0; it < rounds; ++it) {
+        CDL_TW(tw0, mbar_wait_cluster(dempty, (it & 1) ^ 1));       // col2im of the previous tile has drained D0 | D1
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kSChunks; ++c) {                        // slot, barrier parity and every descriptor: constants
+          const int slot = c % kSSlots;
+          CDL_TW(tw1, mbar_wait_cluster(LO ? &aboth[slot] : &afull[slot], c / kSSlots));
           tc_fence_after();
-          const uint32_t dcol = tbase + kColDB + pass * kNBP;
-          for (int c = 0; c < 6; ++c, ++gch) {
-            const uint32_t slot = gch % kASlotsB;
-            CDL_TW(tw1, mbar_wait_cluster(&afull[slot], (gch / kASlotsB) & 1));
-            tc_fence_after();
-            const uint32_t a0 = tbase + kColAB + slot * kASlotB;
-            const uint64_t bd = bdesc0 + (uint64_t)(pass * kKBSteps + c * 4) * kBStep;
-            if (c < 5) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, (c | j) != 0);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 2; ++j) mma_tf32_ts<2>(dcol, a0 + j * 8, bd + (uint64_t)j * kBStep, idesc, 1);
+          for (int j = 0; j < kSChunkKS; ++j) {
+            const int ks = kSChunkKS * c + j;
+            if (ks < kKBSteps) {
+              const uint64_t ad = adesc0 + (uint64_t)((slot * kSChunkFloats * 4 + j * 256) >> 4);
+              mma_tf32_ss_warp<2>(tbase + kColD0, ad, bdesc0 + (uint64_t)ks * kBStep, idesc, ks != 0);
+              mma_tf32_ss_warp<2>(tbase + kColD1, ad, bdesc0 + (uint64_t)(kKBSteps + ks) * kBStep, idesc, ks != 0);
             }
-            mma_commit<2>(&aempty[slot]);             // A slot reusable once these MMAs have read it
           }
-          mma_commit<2>(&dfull[pass]);                // this pass's accumulator is complete -> col2im (both CTAs)
+          mma_commit_warp<2>(&aempty[slot]);          // A slot reusable once these MMAs have read it (both CTAs)
+        }
+        mma_commit_warp<2>(dfull);                    // both accumulators complete -> col2im (both CTAs)
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================== TMA: code tile -> A ring, 8 KB chunks ==============================
+    if (lane == 0) {
+      tma_prefetch_desc(&zmap);
+      const int G = code_groups_per_row(g.Qw);
+      for (int it = 0; it < rounds; ++it) {
+        const SynTile t = syn_tile(p, t0, t1, it);
+        const int g0 = (t.qw0 >> 4) * 2;                             // first group of the tile in its row
+        {                                                            // the next tile's 16 groups are one contiguous run: one L2 prefetch
+          const SynTile t2 = syn_tile(p, t0, t1, it + 1);
+          if (t2.valid) {
+            const int g2 = (t2.qw0 >> 4) * 2, ng = min(kSGroups, G - g2);
+            bulk_prefetch_l2(p.z + ((size_t)t2.row * G + g2) * kCodeGroup, (uint32_t)ng * kCodeGroup * 4);
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < kSChunks; ++c) {
+          const int slot = c % kSSlots;
+          CDL_TW(tw0, mbar_wait(&aempty[slot], (c / kSSlots) ^ 1));
+          if (LO) {
+            // the chunk is transformed in place before the MMA may read it: completion on this CTA's own barrier, then
+            // the col2im warps of both CTAs arrive on the leader's aboth
+            mbar_expect_tx(&afull[slot], kSChunkFloats * 4);
+            tma_load_3d(sA + slot * kSChunkFloats, &zmap, c * kSChunkK4 * kCodeChunk, g0, (int)t.row, &afull[slot]);
+          } else {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+            if (p.dbg_mode & 256) { if (rank == 0) mbar_arrive(&afull[slot]); continue; }
+            if (rank == 0) mbar_expect_tx(&afull[slot], 2 * kSChunkFloats * 4);
+            tma_load_3d_2cta(sA + slot * kSChunkFloats, &zmap, c * kSChunkK4 * kCodeChunk, g0, (int)t.row, &afull[slot]);
+          }
         }
       }
     }
@@ -403,21 +430,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_tc_sy
   }
   if (p.dbg && lane == 0) {
     long long* d = p.dbg + ((size_t)blockIdx.x * 24 + warp) * 8;
-    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2; d[4] = tw3; d[5] = tw4; d[6] = tw5;
+    d[0] = clock64() - tstart; d[1] = tw0; d[2] = tw1; d[3] = tw2;
   }
   tc_fence_before();
   cluster_sync_all();
-  if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
+  if (warp == kSynMmaWarp) tmem_dealloc<2>(tbase, 512);
 }
 
-// ---- code layout conversion: internal quad-blocked channels-last <-> reference (N,M,Qd,Qh,Qw) ----
-// One block = 32 consecutive sites of one row x 32 subbands, transposed through shared memory.  On the internal side
-// that tile is 8 contiguous 512-byte pieces (4 w-blocks x 2 parities, 4 subband blocks each): one float4 per lane.
+// ---- code layout conversion: internal (groups of 8 same-parity sites, pre-biased) <-> reference (N,M,Qd,Qh,Qw) ----
+// One block = 32 consecutive sites of one row (4 groups) x 32 subbands, transposed through shared memory.  On the
+// internal side a thread moves one float4 = 4 subbands of one site; 8 lanes fill a 128-byte chunk.
 // grid = (rows * ceil(Qw/32), 176/32 rounded up, N); R = Qd*Qh rows per sample.
-__device__ __forceinline__ void code_tile_piece(int warp, int lane, int& qloc, int& mloc) {
-  const int wb = warp >> 1, par = warp & 1;                 // piece = (w-block, parity); lane = float4 index inside it
-  qloc = 8 * wb + 2 * ((lane & 7) >> 1) + par;              // site inside the 32-site segment
-  mloc = 8 * (lane >> 3) + 4 * (lane & 1);                  // first of 4 subbands inside the 32-subband slab
+__device__ __forceinline__ void code_tile_piece(int t, int& grp, int& k4l, int& i8, int& qloc) {
+  grp = t >> 6; k4l = (t >> 3) & 7; i8 = t & 7;
+  qloc = 16 * (grp >> 1) + 2 * i8 + (grp & 1);             // site inside the 32-site segment
 }
 __global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ zcl, float* __restrict__ z, int R, int Qw, int M) {
   __shared__ float t[32][33];                               // [site][subband]
@@ -425,12 +451,16 @@ __global__ void __launch_bounds__(256) k_code_export(const float* __restrict__ z
   const int row = blockIdx.x / nseg, qw0 = (blockIdx.x % nseg) * 32;
   const int m0 = blockIdx.y * 32, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int qloc, mloc;
-  code_tile_piece(warp, lane, qloc, mloc);
+  const int G = code_groups_per_row(Qw);
+  int grp, k4l, i8, qloc;
+  code_tile_piece(threadIdx.x, grp, k4l, i8, qloc);
+  const int gidx = (qw0 >> 4) * 2 + grp, k4 = (m0 >> 2) + k4l;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (qw0 + qloc < Qw && m0 + mloc < kKB)
-    v = *reinterpret_cast<const float4*>(zcl + code_site_offset((size_t)n * R + row, Qw, qw0 + qloc) + (size_t)((m0 + mloc) >> 3) * kCodeBlk + ((m0 + mloc) & 7));
-  t[qloc][mloc] = v.x; t[qloc][mloc + 1] = v.y; t[qloc][mloc + 2] = v.z; t[qloc][mloc + 3] = v.w;
+  if (gidx < G && k4 < kCodeK4) {
+    const float4 w = *reinterpret_cast<const float4*>(zcl + (((size_t)n * R + row) * G + gidx) * kCodeGroup + (size_t)k4 * kCodeChunk + i8 * 4);
+    v = make_float4(code_dec(w.x), code_dec(w.y), code_dec(w.z), code_dec(w.w));
+  }
+  t[qloc][4 * k4l] = v.x; t[qloc][4 * k4l + 1] = v.y; t[qloc][4 * k4l + 2] = v.z; t[qloc][4 * k4l + 3] = v.w;
   __syncthreads();
   const size_t Q = (size_t)R * Qw;
   for (int r = warp; r < 32; r += 8) {
@@ -444,17 +474,19 @@ __global__ void __launch_bounds__(256) k_code_import(const float* __restrict__ z
   const int row = blockIdx.x / nseg, qw0 = (blockIdx.x % nseg) * 32;
   const int m0 = blockIdx.y * 32, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = code_groups_per_row(Qw);
   const size_t Q = (size_t)R * Qw;
   for (int r = warp; r < 32; r += 8) {
     const int m = m0 + r, qw = qw0 + lane;
-    t[lane][r] = (m < M && qw < Qw) ? z[((size_t)n * M + m) * Q + (size_t)row * Qw + qw] : 0.0f;
+    t[lane][r] = (m < M && qw < Qw) ? z[((size_t)n * M + m) * Q + (size_t)row * Qw + qw] : 0.0f;     // layout padding = 0
   }
   __syncthreads();
-  int qloc, mloc;
-  code_tile_piece(warp, lane, qloc, mloc);
-  if (qw0 + qloc < Qw && m0 + mloc < kKB)
-    *reinterpret_cast<float4*>(zcl + code_site_offset((size_t)n * R + row, Qw, qw0 + qloc) + (size_t)((m0 + mloc) >> 3) * kCodeBlk + ((m0 + mloc) & 7)) =
-        make_float4(t[qloc][mloc], t[qloc][mloc + 1], t[qloc][mloc + 2], t[qloc][mloc + 3]);
+  int grp, k4l, i8, qloc;
+  code_tile_piece(threadIdx.x, grp, k4l, i8, qloc);
+  const int gidx = (qw0 >> 4) * 2 + grp, k4 = (m0 >> 2) + k4l;
+  if (gidx < G && k4 < kCodeK4)
+    *reinterpret_cast<float4*>(zcl + (((size_t)n * R + row) * G + gidx) * kCodeGroup + (size_t)k4 * kCodeChunk + i8 * 4) =
+        make_float4(code_enc(t[qloc][4 * k4l]), code_enc(t[qloc][4 * k4l + 1]), code_enc(t[qloc][4 * k4l + 2]), code_enc(t[qloc][4 * k4l + 3]));
 }
 
 }  // namespace tc

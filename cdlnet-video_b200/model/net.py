@@ -58,7 +58,8 @@ class _ISTANet(nn.Module):
     #: "auto" picks the fastest kernel family that meets the parity bar (max|xhat - fp32| <= 1e-4) for the geometry AND
     #: the weights: the tcgen05 (tf32 operand) kernels where they exist, after a one-time calibration per set of weights
     #: (`_calibrate`) has shown that they stay inside the bar - otherwise the exact fp32 kernels;
-    #: "fp32" forces the exact CUDA-core kernels, "tf32" forces the tcgen05 path without calibration.
+    #: "fp32" forces the exact CUDA-core kernels, "tf32" / "tf32x3" force the tcgen05 path (single-pass operands / 3-term
+    #: split analysis, 2-D stride-1 geometries) without calibration.
     precision = os.environ.get("CDL_PRECISION", "auto")
     #: `auto` keeps the tensor-core kernels only if, on a calibration crop of the first input, they agree with the exact
     #: fp32 kernels to this max-abs deviation on xhat (the parity bar is 1e-4; the margin covers crop-vs-full variation)
@@ -134,10 +135,10 @@ class _ISTANet(nn.Module):
 
     def _precision_for(self, y, mask, c, key):
         """Kernel family for this input: the module's `precision`, with "auto" resolved per set of weights."""
-        if self.precision == "fp32":
-            return "fp32"
+        if self.precision in ("fp32", "tf32", "tf32x3"):
+            return self.precision
         if self.precision != "auto":
-            return "tf32"
+            raise ValueError(f"unknown precision {self.precision!r}")
         choice = self.__dict__.setdefault("_auto_choice", {})
         ck = (key, tuple(y.shape[1:]), mask is not None)
         if ck not in choice or self.training:
@@ -155,17 +156,23 @@ class _ISTANet(nn.Module):
         yc = y[sl].contiguous()
         mc = None if mask is None else mask[(slice(0, 1),) + sl[1:]].expand_as(yc).contiguous()
         cc = None if c is None else c[:1].contiguous()
-        p_tc = self._plan_for(yc.shape, mc is not None, y.device.index, "tf32")
-        if p_tc.precision != "tf32":
-            return ("tf32", None)        # no tensor-core kernel for this geometry: the request resolves to the fp32 family anyway
-        p_ex = self._plan_for(yc.shape, mc is not None, y.device.index, "fp32")
         A, B = self._filter_banks()
-        outs = []
-        for plan in (p_tc, p_ex):
-            plan.set_weights(A, B, self.t)
-            outs.append(plan.denoise(yc, mc, cc, want_z=False)[0])
-        dev = float((outs[0] - outs[1]).abs().max())
-        return ("tf32" if dev <= self.auto_tolerance else "fp32", dev)
+        p_ex = self._plan_for(yc.shape, mc is not None, y.device.index, "fp32")
+        ref, dev = None, None
+        for family in ("tf32", "tf32x3"):
+            p_tc = self._plan_for(yc.shape, mc is not None, y.device.index, family)
+            if p_tc.precision != family:
+                if family == "tf32":
+                    return ("tf32", None)        # no tensor-core kernel for this geometry: the request resolves to the fp32 family anyway
+                continue                          # no 3-term kernel for this geometry (video): next stop is fp32
+            if ref is None:
+                p_ex.set_weights(A, B, self.t)
+                ref = p_ex.denoise(yc, mc, cc, want_z=False)[0]
+            p_tc.set_weights(A, B, self.t)
+            dev = float((p_tc.denoise(yc, mc, cc, want_z=False)[0] - ref).abs().max())
+            if dev <= self.auto_tolerance:
+                return (family, dev)
+        return ("fp32", dev)
 
     def _c_vector(self, sigma, N, device):
         """c = sigma/255 (model/net.py:82,197) as an fp32 vector of N, rounded like the reference:

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-PREC = {"fp32": 0, "tf32": 1}
+PREC = {"fp32": 0, "tf32": 1, "tf32x3": 2}
 
 
 def _ptr(t):
@@ -81,7 +81,7 @@ class Plan:
 
     @property
     def precision(self):
-        return {0: "fp32", 1: "tf32"}[self.lib.cdl_plan_precision(self.handle)]
+        return {0: "fp32", 1: "tf32", 2: "tf32x3"}[self.lib.cdl_plan_precision(self.handle)]
 
     def set_rearm(self, enable=True):
         """Stepwise drivers only: let analysis_step overwrite its consumed input r with -yp for the next residual synthesis

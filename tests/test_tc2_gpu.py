@@ -13,10 +13,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-experimental = pytest.mark.skipif(os.environ.get("CDL_RUN_EXPERIMENTAL") != "1", reason="not yet validated on hardware: set CDL_RUN_EXPERIMENTAL=1")
-
-
-def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None, syn=None, ana=None):
+def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None, ana=None):
     from cdlnet_video_b200 import Plan
     os.environ.pop("CDL_TC2D", None)
     ref = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="fp32")
@@ -24,18 +21,13 @@ def _plans(N, C, M, K, H, W, mode=None, has_mask=False, maskpass=None, syn=None,
         os.environ["CDL_TC2D"] = mode
     if maskpass is not None:
         os.environ["CDL_TC2D_MASKPASS"] = "1" if maskpass else "0"
-    if syn is not None:
-        os.environ["CDL_TC2D_SYN"] = syn
-    if ana is not None:
-        os.environ["CDL_TC2D_ANA"] = ana
+    prec = "tf32x3" if ana == "3" else "tf32"             # tf32x3 = the 3-term split analysis (CDL_PREC_TF32X3)
     try:
-        tc = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision="tf32")
+        tc = Plan(2, N, C, M, K, (H, W), (7, 7), 1, has_mask=has_mask, precision=prec)
     finally:
         os.environ.pop("CDL_TC2D", None)
         os.environ.pop("CDL_TC2D_MASKPASS", None)
-        os.environ.pop("CDL_TC2D_SYN", None)
-        os.environ.pop("CDL_TC2D_ANA", None)
-    assert ref.precision == "fp32" and tc.precision == "tf32"
+    assert ref.precision == "fp32" and tc.precision == prec
     return ref, tc
 
 
@@ -44,16 +36,14 @@ def test_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
     _analysis_bit_exact(N, C, M, H, W, None)
 
 
-@experimental
 @pytest.mark.parametrize("N,C,M,H,W", [(2, 3, 64, 40, 72), (1, 3, 20, 21, 44), (3, 2, 64, 128, 256), (1, 1, 8, 16, 16)])
 def test_analysis_x3_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W):
-    """The candidate 3-term analysis (cdl_tc2_analysis_x3.cuh, CDL_TC2D_ANA=3): on exactly representable data the lo
+    """The 3-term analysis (cdl_tc2_analysis_x3.cuh, precision "tf32x3"): on exactly representable data the lo
     parts vanish and the result must still equal the fp32 kernel's bit for bit (eight-copy shifter, single operand
     buffer, three MMAs per K-step)."""
     _analysis_bit_exact(N, C, M, H, W, "3")
 
 
-@experimental
 def test_analysis_x3_forward_close_to_oracle():
     """With the 3-term analysis the forward error is the residual synthesis's alone: well under the single-pass 3.1e-5."""
     ex = _forward_cfg1b_like("1", ana="3")       # tensor-core analysis only (exact fp32 synthesis): ~1e-6 expected
@@ -97,23 +87,14 @@ def _analysis_bit_exact(N, C, M, H, W, ana):
     (2, 3, 64, 40, 72, True, False), (1, 3, 48, 64, 128, True, False)])    # ... or inside the footprint flush (CDL_TC2D_MASKPASS=0)
 def test_synthesis_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask, maskpass):
     """Residual synthesis mask * B z - yp on the tensor cores (default family) vs the exact fp32 kernel, exact data."""
-    _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass, None)
+    _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass)
 
 
-@experimental
-@pytest.mark.parametrize("N,C,M,H,W,use_mask,maskpass", [
-    (2, 3, 64, 40, 72, True, None), (1, 3, 20, 21, 44, False, None), (3, 2, 64, 128, 256, False, None), (1, 1, 32, 16, 32, False, None),
-    (1, 1, 8, 16, 16, False, None), (1, 3, 48, 64, 128, True, False)])
-def test_synthesis_v2_integer_data_bit_exact_vs_fp32_kernel(N, C, M, H, W, use_mask, maskpass):
-    """The candidate col2im (cdl_tc2_synthesis_v2.cuh, CDL_TC2D_SYN=2): same bar as the default kernel."""
-    _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass, "2")
-
-
-def _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass, syn):
+def _synthesis_bit_exact(N, C, M, H, W, use_mask, maskpass):
     torch.manual_seed(N * 100 + C * 10 + M + 1)
     dev = torch.device("cuda", 0)
     K = 2
-    ref, tc = _plans(N, C, M, K, H, W, has_mask=use_mask, maskpass=maskpass, syn=syn)
+    ref, tc = _plans(N, C, M, K, H, W, has_mask=use_mask, maskpass=maskpass)
     Bw = [torch.randint(-4, 5, (M, C, 7, 7), device=dev).float() / 8 for _ in range(K)]
     t = torch.zeros(K, 2, M, device=dev)
     for pl in (ref, tc):
@@ -159,20 +140,17 @@ def _forward_cfg1b_like(mode, ana=None):
     y = torch.rand(2, 1, 64, 96)
     xr, zr, *_ = O.forward_t(y, [m.weight.detach() for m in net.A], [m.weight.detach() for m in net.B], net.t.detach(), 1, 25.0, True, 1)
     net = net.cuda().eval()
-    net.precision = "tf32"
+    net.precision = "tf32x3" if ana == "3" else "tf32"
     if mode is not None:
         os.environ["CDL_TC2D"] = mode
-    if ana is not None:
-        os.environ["CDL_TC2D_ANA"] = ana
     try:
         with torch.no_grad():
             xhat, z = net(y.cuda(), 25.0)
         torch.cuda.synchronize()
     finally:
         os.environ.pop("CDL_TC2D", None)
-        os.environ.pop("CDL_TC2D_ANA", None)
-    plan = next(reversed(net._plans.values()))
-    assert plan.precision == "tf32"
+    plan = net._last_plan
+    assert plan.precision == net.precision
     ex = (xhat.cpu() - xr).abs().max().item()
     print(f"tc2 forward (CDL_TC2D={mode}, CDL_TC2D_ANA={ana}): max|xhat-oracle|={ex:.3e} max|z-oracle|={(z.cpu() - zr).abs().max().item():.3e}")
     return ex
