@@ -11,7 +11,7 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libcdl_b200.so")
+LIB_PATH = os.environ.get("CDL_LIB_PATH") or os.path.join(HERE, "libcdl_b200.so")     # CDL_LIB_PATH: an alternate build (e.g. -DCDL_TC_PROFILE)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

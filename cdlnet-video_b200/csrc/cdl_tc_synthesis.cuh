@@ -196,15 +196,19 @@ template <int ROW0, int NROWS, int DONE = 0, typename Rel>
 __device__ __forceinline__ void c2i_part(uint32_t acol, uint32_t (&u)[32], float* xs, float* ss, int pbase, int colbase, int q, const C2iLane& L,
                                          Rel released) {
   using namespace ptx;
-  if constexpr (DONE == 0) tmem_ld32(acol, u);
+#ifndef CDL_SYN_EXP
+#define CDL_SYN_EXP 0      // experiments (results invalid): 1 = TMEM reads only, 2 = everything but the TMEM reads
+#endif
+  if constexpr (DONE == 0 && CDL_SYN_EXP != 2) tmem_ld32(acol, u);
   constexpr int NR = (NROWS - DONE) < 4 ? (NROWS - DONE) : 4;
   tmem_wait_ld();
   uint32_t v[7 * NR];
 #pragma unroll
   for (int i = 0; i < 7 * NR; ++i) v[i] = u[i];
-  if constexpr (DONE + NR < NROWS) tmem_ld32(acol + 7 * (DONE + NR), u);
+  if constexpr (DONE + NR < NROWS) { if constexpr (CDL_SYN_EXP != 2) tmem_ld32(acol + 7 * (DONE + NR), u); }
   else released();
-  c2i_rows<ROW0 + DONE, NR>(v, xs, ss, pbase, colbase, q, L);
+  if constexpr (CDL_SYN_EXP != 1) c2i_rows<ROW0 + DONE, NR>(v, xs, ss, pbase, colbase, q, L);
+  else if (v[0] == 0x7fc12345u) xs[0] = 1.0f;        // keep the loads alive
   if constexpr (DONE + NR < NROWS) c2i_part<ROW0, NROWS, DONE + NR>(acol, u, xs, ss, pbase, colbase, q, L, released);
 }
 
@@ -315,6 +319,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
         __syncwarp();
         if (lane == 0) { if (rank == 0) mbar_arrive(dempty); else mbar_arrive_cluster(dempty, 0); }
       };
+#ifdef CDL_TC_PROFILE
+      const long long tc0 = clock64();
+#endif
       if (t.valid && !(p.dbg_mode & 64)) {
         uint32_t u[32];
         switch (part) {                                            // warp-uniform: a quarter of the 49 rows each
@@ -326,6 +333,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
       } else {
         release();
       }
+#ifdef CDL_TC_PROFILE
+      const long long tc1 = clock64();
+      tw1 += tc1 - tc0;
+#endif
       named_bar_sync(1, 32 * kSynC2iWarps);                        // every warp's rows are in the ring
       if (t.valid && !(p.dbg_mode & 128)) {
         // fine rows 2*qh and 2*qh+1 are final (all 7 at the end of a run): out += row, clear the ring slot.  Runs while
@@ -360,6 +371,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
         }
       }
       named_bar_sync(1, 32 * kSynC2iWarps);   // the flushed rows are clear before the next tile's col2im reuses their ring slots
+#ifdef CDL_TC_PROFILE
+      tw2 += clock64() - tc1;
+#endif
     }
   } else if (warp == kSynMmaWarp) {
     // ============================== MMA issue (leader CTA; converged warp, elected lane) ==============================

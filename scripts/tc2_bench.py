@@ -57,20 +57,15 @@ def main():
             net.__dict__.pop("_plans", None)
             os.environ["CDL_TC2D"] = "0" if tag == "fp32" else "2"
             os.environ.pop("CDL_TC2D_MASKPASS", None)
-            os.environ.pop("CDL_TC2D_SYN", None)
             if tag == "tc2fm":
                 os.environ["CDL_TC2D_MASKPASS"] = "0"
-            if tag == "tc2v2":
-                os.environ["CDL_TC2D_SYN"] = "2"
-            os.environ.pop("CDL_TC2D_ANA", None)
-            if tag == "tc2x3":
-                os.environ["CDL_TC2D_ANA"] = "3"
+            net.precision = "fp32" if tag == "fp32" else ("tf32x3" if tag == "tc2x3" else "tf32")
 
             def fwd():
                 with torch.no_grad():
                     return net(y, sigma, mask=mask)
             ms, (xhat, z) = timed(fwd)
-            plan = next(iter(net._plans.values()))
+            plan = net._last_plan
             res[f"{tag}_precision"] = plan.precision
             res[f"{tag}_forward_ms"] = ms
             outs[tag] = (xhat, (z != 0).float().mean().item())
@@ -89,8 +84,6 @@ def main():
             del zz, r, yp, mp
         os.environ.pop("CDL_TC2D", None)
         os.environ.pop("CDL_TC2D_MASKPASS", None)
-        os.environ.pop("CDL_TC2D_SYN", None)
-        os.environ.pop("CDL_TC2D_ANA", None)
         vox = shape[0] * shape[2] * shape[3]
         for tag in arms:
             res[f"{tag}_Mpix_s"] = vox / (res[f"{tag}_forward_ms"] * 1e-3) / 1e6

@@ -73,7 +73,7 @@ def _run(name, kind, hp, shape, sigma, use_mask=False, gain=1.0, expect=None, ts
     assert ex <= 1e-4, ex
     assert abs(ps - pr) <= 0.01
     if expect is not None:
-        assert plan.precision == expect, (plan.precision, cal)
+        assert plan.precision in ((expect,) if isinstance(expect, str) else expect), (plan.precision, cal)
     return ex
 
 
@@ -82,7 +82,9 @@ def test_cfg1_cdlnet_s2030():
 
 
 def test_cfg1b_root_args():
-    _run("cfg1b", "cdl", (20, 32, 7, 1, 1), (1, 1, 256, 256), 25.0, expect="tf32")
+    # protocol weights: single-pass tf32 measures 7.8e-5 here (inside the bar, outside `auto`'s 6.5e-5 margin): auto moves to the
+    # 3-term analysis (tf32x3), still on the tensor cores
+    _run("cfg1b", "cdl", (20, 32, 7, 1, 1), (1, 1, 256, 256), 25.0, expect=("tf32", "tf32x3"))
 
 
 def test_cfg3_jdd_k42_mask_per_sample_sigma():

@@ -143,20 +143,10 @@ SHDR = os.path.join(os.path.dirname(HDR), "cdl_tc2_synthesis.cuh")
 SSRC = open(SHDR).read()
 
 
-def test_synthesis_constants_and_lockstep():
+def test_synthesis_constants():
     assert "constexpr int kSTH = 4, kSTW = 32;" in SSRC and "constexpr int kSN = 176;" in SSRC
-    assert "const int th = (t + r) % kP;" in SSRC
-    assert "float* row = sX + (c * kFY + r + th) * kFPitch;" in SSRC
     assert "__shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);" in SSRC
-    assert "if (lane >= tw) own += w; else spill += w;" in SSRC and "if (lane < kP - 1) row[32 + lane] += spill;" in SSRC
     assert "const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;" in SSRC
-    # at every step the four col2im warps (tile rows r) write four DIFFERENT footprint rows r + th
-    for t in range(7):
-        rows = [r + (t + r) % 7 for r in range(4)]
-        assert len(set(rows)) == 4 and max(rows) <= 9
-    # and every warp visits every th exactly once
-    for r in range(4):
-        assert sorted((t + r) % 7 for t in range(7)) == list(range(7))
     # TMEM budget: two accumulators + two A slots
     assert 2 * 176 + 2 * 64 <= 512
 
@@ -175,58 +165,13 @@ def _pack_syn(w, Kg):
     return out
 
 
-@pytest.mark.parametrize("C,M,H,W", [(1, 32, 9, 40), (3, 64, 12, 72), (3, 20, 7, 44)])
-def test_synthesis_gemm_col2im_equals_conv_transpose2d(C, M, H, W):
-    rng = np.random.default_rng(C * 100 + M)
-    z = rng.integers(-4, 5, size=(M, H, W)).astype(np.float32)
-    w = rng.integers(-4, 5, size=(M, C, 7, 7)).astype(np.float32)
-    want = torch.nn.functional.conv_transpose2d(torch.from_numpy(z)[None], torch.from_numpy(w), padding=3)[0].numpy()
-    Kg = (M + 15) // 16 * 16
-    pack = _pack_syn(w, Kg)
-    out = np.zeros((C, H, W), np.float32)
-    for h0 in range(0, H, 4):
-        for w0 in range(0, W, 32):
-            A = np.zeros((128, Kg), np.float32)                 # TMEM A slot: lane = 32*row + w, column = subband
-            for lane in range(128):
-                r, x = divmod(lane, 32)
-                if h0 + r < H and w0 + x < W:
-                    A[lane, :M] = z[:, h0 + r, w0 + x]
-            D = np.zeros((128, 176), np.float32)
-            for ks in range(Kg // 8):                           # B descriptor: start + ks*176*32 B, LBO 128 B, SBO 256 B
-                Bm = np.zeros((176, 8), np.float32)
-                for n in range(176):
-                    for j in range(8):
-                        Bm[n, j] = pack[ks * 176 * 8 + (n // 8) * 64 + (j // 4) * 32 + (n % 8) * 4 + (j % 4)]
-                D += A[:, 8 * ks:8 * ks + 8] @ Bm.T
-            fp = np.zeros((C, 10, 40), np.float32)              # col2im into the footprint, then the flush
-            for r in range(4):
-                for c in range(C):
-                    for t in range(7):
-                        th = (t + r) % 7
-                        v = D[32 * r:32 * r + 32, (c * 7 + th) * 8:(c * 7 + th) * 8 + 8]     # [lane][tw]
-                        own, spill = v[:, 0].copy(), np.zeros(32, np.float32)
-                        for tw in range(1, 7):                  # rotate-shuffle: lane L receives tap tw of lane (L - tw) & 31
-                            w_ = v[(np.arange(32) - tw) & 31, tw]
-                            own += np.where(np.arange(32) >= tw, w_, 0)
-                            spill += np.where(np.arange(32) < tw, w_, 0)
-                        fp[c, r + th, :32] += own
-                        fp[c, r + th, 32:38] += spill[:6]
-            for c in range(C):
-                for y in range(10):
-                    for x in range(38):
-                        gh, gw = h0 - 3 + y, w0 - 3 + x
-                        if 0 <= gh < H and 0 <= gw < W:
-                            out[c, gh, gw] += fp[c, y, x]
-    assert np.array_equal(out, want)
-
-
 # ------------------------------------------------------------------------------------------------------------
-# candidate col2im of cdl_tc2_synthesis_v2.cuh: write-once private footprints, overlap-add in the flush
+# col2im of k_tc2_synthesis: write-once private footprints, overlap-add in the flush
 # ------------------------------------------------------------------------------------------------------------
-V2SRC = open(os.path.join(os.path.dirname(HDR), "cdl_tc2_synthesis_v2.cuh")).read()
+V2SRC = SSRC
 
 
-def test_synthesis_v2_source_matches_model():
+def test_synthesis_source_matches_model():
     assert "if (th >= 0 && th < kP) v += pv[r * kPrivWarp + (c * kP + th) * kFPitch + x];" in V2SRC
     assert "row[lane] = own;" in V2SRC and "if (lane < kP - 1) row[32 + lane] = spill;" in V2SRC
     assert "put_row(&cur[8 * q], priv + (4 * g + q) * kFPitch);" in V2SRC
@@ -236,7 +181,7 @@ def test_synthesis_v2_source_matches_model():
 
 
 @pytest.mark.parametrize("C,M,H,W", [(1, 32, 9, 40), (3, 64, 12, 72), (2, 20, 7, 44)])
-def test_synthesis_v2_private_footprints_equal_conv_transpose2d(C, M, H, W):
+def test_synthesis_private_footprints_equal_conv_transpose2d(C, M, H, W):
     rng = np.random.default_rng(C * 100 + M + 7)
     z = rng.integers(-4, 5, size=(M, H, W)).astype(np.float32)
     w = rng.integers(-4, 5, size=(M, C, 7, 7)).astype(np.float32)
@@ -286,7 +231,7 @@ def test_synthesis_v2_private_footprints_equal_conv_transpose2d(C, M, H, W):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# candidate 3-term analysis (cdl_tc2_analysis_x3.cuh): generated from k_tc2_analysis, eight operand copies
+# 3-term analysis (cdl_tc2_analysis_x3.cuh, precision "tf32x3"): k_tc2_analysis with eight operand copies
 # ------------------------------------------------------------------------------------------------------------
 def test_analysis_x3_is_the_validated_kernel_plus_three_edits():
     x3 = open(os.path.join(os.path.dirname(HDR), "cdl_tc2_analysis_x3.cuh")).read()
