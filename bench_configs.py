@@ -140,7 +140,7 @@ def main():
             with torch.no_grad():
                 return net(y, sigma, mask=mask)
         ms = time_steps(fn, args.steps, args.warmup, world)
-        plan = next(iter(net._plans.values()))
+        plan = net._last_plan
         vox = world * shape[0] * shape[2] * shape[3]
         flops = 2 * K * 2.0 * (vox / s ** 2) * M * C * P * P
         # z makes one HBM round trip per iteration; images: preprocess 2 reads, K reads of yp (+ K-1 of the
