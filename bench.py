@@ -510,12 +510,15 @@ def run_cfg5(args, rank, world, local):
             peaks, peak_src = load_peaks()
             tf32_meas = measure_tf32_peak(torch, dev) if world == 1 else None
             tk = {k: [a.elapsed_time(b) for a, b in v] for k, v in acc.items()}
-            xch_ms = sum(tk.pop("exchange"))
+            xl = sorted(tk.pop("exchange"))
+            xch_ms = sum(xl)
             Vr = (g["q1"] - g["q0"]) * s * H * W                 # this rank's owned voxels
             alg = algorithmic(1, ((g["q1"] - g["q0"]) * s, H, W))
             alg["V_rank"] = Vr
             roof = roofline_from_times(tk, alg, peaks, peak_src, plan.precision, f"{(g['q1'] - g['q0']) * s}x{H}x{W}", tf32_meas)
             roof["exchange_ms_per_step"] = xch_ms
+            roof["exchange_ms"] = {"min": xl[0], "median": xl[len(xl) // 2], "max": xl[-1], "n": len(xl),
+                                   "bytes_per_direction_per_seam": den.plan.halo_bytes}
             roof["rank"] = 0
         del yp
 
