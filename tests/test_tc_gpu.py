@@ -102,7 +102,9 @@ def test_code_layout_roundtrip(dims, N, M):
 def test_stepwise_equals_fused_tf32():
     """cdl_forward (which fuses the -yp re-arm of the residual buffer into the rounding pass) == the step API driven
     from the host, on the tensor-core path.  The scatter-add order differs run to run (atomics), and a flipped
-    soft-threshold decision moves z by a threshold: compare at 5e-5 (bench.py sees up to 3e-5 between two runs at K=30)."""
+    soft-threshold decision moves z by a threshold: two runs of the SAME path differ by up to ~5.5e-5 on xhat (measured:
+    scripts/rearm_spread.py, profiles/r02n_pytest_summary.log), so the two drivers are compared at the parity bar (1e-4)
+    and each of them against the oracle at the same bar in test_tf32_small_vs_oracle."""
     d = torch.device("cuda", 0)
     dims, N, M, K = (8, 32, 64), 2, 169, 4
     A, B, g = _weights(M, K, 3, 0.7 / np.sqrt(2.0 * M * 343 / 8))
@@ -121,8 +123,8 @@ def test_stepwise_equals_fused_tf32():
     xp = torch.empty_like(yp)
     plan.synthesis_step(0, code, xp, residual=False)
     x2 = plan.postprocess(xp, mean)
-    assert (x2 - xhat).abs().max().item() <= 5e-5
-    assert (plan.export_code(code) - z).abs().max().item() <= 5e-5
+    assert (x2 - xhat).abs().max().item() <= 1e-4
+    assert (plan.export_code(code) - z).abs().max().item() <= 1e-4
 
 
 def test_stepwise_rearm_opt_in():
@@ -152,5 +154,5 @@ def test_stepwise_rearm_opt_in():
         launches.append(plan.launch_count() - n0)
         outs.append((plan.postprocess(r, mean), plan.export_code(code)))
     assert launches[1] == launches[0] - (K - 2)        # synthesis k = 2..K-1 skipped its -yp pass
-    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 5e-5      # run-to-run scatter-add order, as above
-    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 5e-5
+    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 1e-4      # run-to-run scatter-add order, as above
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-4
