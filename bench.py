@@ -328,8 +328,10 @@ def roofline_from_times(tk, alg, peaks, peak_src, eff, n_units, tf32_meas):
     traffic = None
     try:                                     # DRAM bytes per launch of this kernel from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        if eff == "tf32" and tj.get("units") == n_units:
-            traffic = tj[dom]["dram_bytes_per_launch"]
+        for cap in tj.get("captures", []):     # the capture of THIS workload size (per-launch bytes do not scale otherwise)
+            if eff == "tf32" and cap.get("units") == n_units and dom in cap:
+                traffic = cap[dom]["dram_bytes_per_launch"]
+                break
     except Exception:
         pass
     bound = "tensor" if dom == "synthesis" else "hbm"
