@@ -153,6 +153,10 @@ def load():
         lib.cdl_halo_add.argtypes = [vp] * 6
         lib.cdl_forward_sharded.restype = i32
         lib.cdl_forward_sharded.argtypes = [vp] * 9
+        lib.cdl_nle_mad_workspace_bytes.restype = i32
+        lib.cdl_nle_mad_workspace_bytes.argtypes = [i32, i32, i32, i32, P(ctypes.c_size_t)]
+        lib.cdl_nle_mad.restype = i32
+        lib.cdl_nle_mad.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
         if lib.cdl_abi_version() != 1:
             raise RuntimeError("libcdl_b200.so ABI version mismatch")
         _lib = lib

@@ -16,6 +16,8 @@
 #include "cdl_prepost.cuh"
 #include "cdl_tc_analysis.cuh"
 #include "cdl_tc_synthesis.cuh"
+#include "cdl_tc_synthesis_h.cuh"
+#include "cdl_nle.cuh"
 #include "cdl_tc2_analysis.cuh"
 #include "cdl_tc2_analysis_x3.cuh"
 #include "cdl_tc2_synthesis.cuh"
@@ -73,12 +75,12 @@ static int make_fine_tmap(CUtensorMap* out, const float* base, const Geo& g, int
 // code of the video tensor-core path viewed as (rows, groups per row, 1408 floats per group): a box is one A-ring chunk
 // of the synthesis kernel, 4 chunks of 4 subbands (512 contiguous bytes) x 16 groups of one row; groups beyond the row
 // and rows beyond the tensor read as zero
-static int make_code_tmap(CUtensorMap* out, const float* code, const Geo& g) {
+static int make_code_tmap(CUtensorMap* out, const float* code, const Geo& g, int chunk_k4 = tc::kSChunkK4) {
   const cuuint64_t G = (cuuint64_t)tc::code_groups_per_row(g.Qw);
   const cuuint64_t rows = (cuuint64_t)g.N * g.Qd * g.Qh;
   const cuuint64_t gdim[3] = {(cuuint64_t)tc::kCodeGroup, G, rows};
   const cuuint64_t gstr[2] = {(cuuint64_t)tc::kCodeGroup * 4, G * tc::kCodeGroup * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)(tc::kSChunkK4 * tc::kCodeChunk), (cuuint32_t)tc::kSGroups, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)(chunk_k4 * tc::kCodeChunk), (cuuint32_t)tc::kSGroups, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(code), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -124,6 +126,8 @@ struct cdl_plan {
   size_t wA_layer, wB_layer;
   // tcgen05 path (3D, P = 7^3, s = 2, C = 1)
   bool tc_ana, tc_syn;
+  bool syn_h;          // synthesis kernel form: tap half per CTA with double-buffered accumulators (cdl_tc_synthesis_h.cuh; default) or
+                       // the cta_group::2 pair form (cdl_tc_synthesis.cuh; CDL_SYN_H=0)
   float* wAtc;         // [K][2 ranks][43][88*8] tf32 filters in UMMA layout
   float* wBtc;         // [K][2 ranks][176*176]
   float* wBtc_lo;      // layer 0 only: tf32(W - tf32(W)), for the 3-term final synthesis
@@ -307,6 +311,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   memset(p, 0, sizeof(*p));
   p->desc = *d;
   p->dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
+  p->syn_h = getenv("CDL_SYN_H") ? atoi(getenv("CDL_SYN_H")) != 0 : true;
   const int s = d->s;
   const bool slab = d->halo_front || d->halo_back;
 
@@ -447,6 +452,8 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
         (e = cudaMalloc(&p->wBtc_lo, p->wBtc_layer * sizeof(float))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc::h::k_tc_synthesis_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::h::kSmemBytesH)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute((const void*)tc::h::k_tc_synthesis_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::h::kSmemBytesH)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kAnaSmemBytes)) != cudaSuccess) {
       cdl_plan_destroy(p);
       return CDL_CUDA_ERROR_BASE + (int)e;
@@ -624,10 +631,12 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
     if (p->tc_ana) {
       tc::k_pack_tc_analysis<<<64, 256, 0, st>>>(A[k], p->wAtc + (size_t)k * p->wAtc_layer, g.M);
       CDL_LAUNCH_CHECK(p);
-      tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M, 0);
+      if (p->syn_h) tc::h::k_pack_tc_synthesis_h<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M, 0);
+      else tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M, 0);
       CDL_LAUNCH_CHECK(p);
       if (k == 0) {
-        tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
+        if (p->syn_h) tc::h::k_pack_tc_synthesis_h<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
+        else tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
         CDL_LAUNCH_CHECK(p);
       }
     }
@@ -874,16 +883,33 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.ntiles = a.nrows * a.tiles_w;
     a.dbg = g_tc_dbg;
     a.dbg_mode = p->dbg_mode;
+    const CUtensorMap* zmap;
+    { const int k4 = p->syn_h ? tc::h::kChK4 : tc::kSChunkK4;      // box = one A-ring slot of the kernel form in use
+      int rc = cached_tmap(p, z, -k4, [&](CUtensorMap* m) { return make_code_tmap(m, z, p->g, k4); }, &zmap); if (rc) return rc; }
+    const bool dz3 = !residual && k == 0;
+    // Final dictionary synthesis xphat = D z (model/net.py:90,210): its tf32 rounding lands directly on xhat and
+    // dominates the output error (measured: 7e-5 of 8e-5), so the two dropped cross terms are added back:
+    //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)       (the scatter-add accumulates the three launches)
+    if (p->syn_h) {
+      long long pairs = p->sm_count / 2;
+      if (pairs > a.ntiles) pairs = a.ntiles;                      // both CTAs of a pair sweep the pair's whole tile range
+      const int grid = 2 * (int)pairs;
+      tc::h::k_tc_synthesis_h<false><<<grid, tc::h::kThreadsH, tc::h::kSmemBytesH, st>>>(a, *zmap);
+      CDL_LAUNCH_CHECK(p);
+      if (dz3) {
+        tc::h::k_tc_synthesis_h<true><<<grid, tc::h::kThreadsH, tc::h::kSmemBytesH, st>>>(a, *zmap);
+        CDL_LAUNCH_CHECK(p);
+        a.wpack = p->wBtc_lo;
+        tc::h::k_tc_synthesis_h<false><<<grid, tc::h::kThreadsH, tc::h::kSmemBytesH, st>>>(a, *zmap);
+        CDL_LAUNCH_CHECK(p);
+      }
+      return CDL_OK;
+    }
     long long pairs = p->sm_count / 2;
     if (pairs > (a.ntiles + 1) / 2) pairs = (a.ntiles + 1) / 2;
-    const CUtensorMap* zmap;
-    { int rc = cached_tmap(p, z, -1, [&](CUtensorMap* m) { return make_code_tmap(m, z, p->g); }, &zmap); if (rc) return rc; }
     tc::k_tc_synthesis<false><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);
     CDL_LAUNCH_CHECK(p);
-    if (!residual && k == 0) {
-      // Final dictionary synthesis xphat = D z (model/net.py:90,210): its tf32 rounding lands directly on xhat and
-      // dominates the output error (measured: 7e-5 of 8e-5), so the two dropped cross terms are added back:
-      //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)       (the scatter-add accumulates the three launches)
+    if (dz3) {
       tc::k_tc_synthesis<true><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);
       CDL_LAUNCH_CHECK(p);
       a.wpack = p->wBtc_lo;
@@ -1149,5 +1175,50 @@ extern "C" int cdl_denoise_host(cdl_plan_t* p, const float* y_host, const float*
   if (rc) return rc;
   CDL_CUDA(cudaMemcpyAsync(xhat_host, xhat, in_bytes, cudaMemcpyDeviceToHost, st));
   if (z_host) CDL_CUDA(cudaMemcpyAsync(z_host, z, z_bytes, cudaMemcpyDeviceToHost, st));
+  return CDL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// blind noise level on the device (reference model/nle.py:17-27, call site analyze.py / analyze3d.py:118-121)
+// ------------------------------------------------------------------------------------------------
+static inline size_t nle_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int cdl_nle_mad_workspace_bytes(int N, int C, int H, int W, size_t* out) {
+  if (!out) return CDL_ERR_NULL;
+  if (N <= 0 || C <= 0 || H < nle::kL || W < nle::kL) return CDL_ERR_SHAPE;
+  const size_t Ho = (size_t)(H - nle::kL) / 2 + 1, Wo = (size_t)(W - nle::kL) / 2 + 1;
+  if ((size_t)C * Ho * Wo >= 0xffffffffull) return CDL_ERR_SHAPE;            // 32-bit ranks
+  *out = nle_align((size_t)N * sizeof(nle::State)) + nle_align((size_t)N * nle::kBins * sizeof(unsigned)) +
+         nle_align((size_t)N * C * Ho * Wo * sizeof(float));
+  return CDL_OK;
+}
+
+extern "C" int cdl_nle_mad(const float* y, int N, int C, int H, int W, float* sigma_hat, void* ws, void* stream_) {
+  if (!y || !sigma_hat) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  size_t need = 0;
+  { int rc = cdl_nle_mad_workspace_bytes(N, C, H, W, &need); if (rc) return rc; }
+  if ((reinterpret_cast<uintptr_t>(ws) & 15)) return CDL_ERR_ALIGN;
+  if (N > 65535 || C > 65535) return CDL_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int Ho = (H - nle::kL) / 2 + 1, Wo = (W - nle::kL) / 2 + 1;
+  char* w = (char*)ws;
+  nle::State* state = reinterpret_cast<nle::State*>(w);
+  unsigned* hist = reinterpret_cast<unsigned*>(w + nle_align((size_t)N * sizeof(nle::State)));
+  float* mag = reinterpret_cast<float*>(w + nle_align((size_t)N * sizeof(nle::State)) + nle_align((size_t)N * nle::kBins * sizeof(unsigned)));
+  const long long per = (long long)C * Ho * Wo;
+  CDL_CUDA(cudaMemsetAsync(hist, 0, (size_t)N * nle::kBins * sizeof(unsigned), st));
+  const int tiles_w = ceil_div(Wo, nle::kTW), tiles_h = ceil_div(Ho, nle::kTH);
+  nle::k_nle_coeffs<<<dim3(tiles_w * tiles_h, C, N), 256, 0, st>>>(y, mag, hist, C, H, W, Ho, Wo, tiles_w);
+  CDL_CUDA(cudaGetLastError());
+  long long hb = (per + 256 * 8 - 1) / (256 * 8); if (hb > 148 * 4) hb = 148 * 4; if (hb < 1) hb = 1;
+  for (int level = 0; level < 3; ++level) {
+    if (level > 0) {
+      nle::k_nle_hist<<<dim3((int)hb, N), 256, 0, st>>>(mag, state, hist, per, level);
+      CDL_CUDA(cudaGetLastError());
+    }
+    nle::k_nle_scan<<<N, 256, 0, st>>>(hist, state, level, (unsigned)per, sigma_hat);
+    CDL_CUDA(cudaGetLastError());
+  }
   return CDL_OK;
 }

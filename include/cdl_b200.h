@@ -170,6 +170,14 @@ int  cdl_halo_add(cdl_plan_t* plan, float* r, const float* recv_prev, const floa
 int  cdl_forward_sharded(cdl_plan_t* plan, cdl_comm_t* comm, const float* yp, const float* c, float* code, float* r,
                          void* halo_ws, void* workspace, void* stream);
 
+/* ---- blind noise level on the device.  Replaces model/nle.py:17-27 `nle_mad` (call sites analyze.py:
+ * `255 * model.nle.noise_level(noisy, method=blind)`, analyze3d.py:118-121):
+ *     sigma_hat[n] = median(|HH * y[n]|) / 0.6745,   HH = diagonal bior4.4 detail filter (model/wvlt.py:5-42), stride 2,
+ * no padding, per channel; lower median over all C x Ho x Wo coefficients (torch.median).  y is (N,C,H,W) fp32 on the
+ * device, H, W >= 10; sigma_hat (N) stays on the device (the modules take sigma as a tensor).  Not bound to a plan.    */
+int cdl_nle_mad_workspace_bytes(int N, int C, int H, int W, size_t* out);
+int cdl_nle_mad(const float* y, int N, int C, int H, int W, float* sigma_hat, void* workspace, void* stream);
+
 /* Number of kernels launched by this plan since creation (bench.py's gpu_launches).               */
 int cdl_plan_launch_count(const cdl_plan_t* plan, uint64_t* out);
 

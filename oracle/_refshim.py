@@ -59,6 +59,36 @@ def load():
     return ref_net
 
 
+def load_nle(filter_bank):
+    """Returns the reference's `model.nle` module.  Its `model.wvlt` imports PyWavelets (absent here): a stub
+    `pywt` whose Wavelet('bior4.4').filter_bank is `filter_bank` stands in, so that everything the reference does WITH
+    the coefficients (outer products, flips, conv2d, median) is the reference's own code."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF}")
+    sys.dont_write_bytecode = True
+    stub = types.ModuleType("pywt")
+
+    class Wavelet:
+        def __init__(self, name):
+            if name != "bior4.4":
+                raise ValueError(name)
+            self.filter_bank = filter_bank
+    stub.Wavelet = Wavelet
+    saved = {k: v for k, v in sys.modules.items() if k == "model" or k.startswith("model.") or k in ("utils", "pywt")}
+    for k in saved:
+        del sys.modules[k]
+    sys.modules["pywt"] = stub
+    sys.path.insert(0, REF)
+    try:
+        import model.nle as ref_nle          # noqa
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.") or k in ("utils", "pywt")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return ref_nle
+
+
 def fix_gdlnet(net):
     """wrap the private `_output_padding` of every Gabor layer."""
     for mod in list(net.A) + list(net.B):

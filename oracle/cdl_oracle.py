@@ -378,3 +378,41 @@ def psnr(x, ref) -> float:
     x = np.asarray(x, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     return float(-10.0 * np.log10(np.mean((x - ref) ** 2)))
+
+
+# ------------------------------------------------------------------------------------------------
+# blind noise level (reference model/nle.py:17-27 nle_mad, model/wvlt.py:5-42) - SURVEY.md 8f N3
+# ------------------------------------------------------------------------------------------------
+# pywt.Wavelet('bior4.4').dec_hi: the reference reads it from PyWavelets at run time (model/wvlt.py:9; the dependency is
+# unpinned and absent from this image).  Values = sqrt(2) x the published CDF 9/7 7-tap high-pass, zero-padded to the
+# 10-tap length pywt uses for bior4.4.  PARITY UNPINNED at the level of these ten numbers (no pywt here to read them
+# from); everything downstream of them is pinned by tests/golden/nle_mad.npz, generated by the reference's own
+# model/nle.py + model/wvlt.py with a stub `pywt` that serves this table (oracle/gen_golden.py nle).
+BIOR44_DEC_HI = (0.0, -0.06453888262869706, 0.04068941760916406, 0.41809227322161724, -0.7884856164055829,
+                 0.41809227322161724, 0.04068941760916406, -0.06453888262869706, 0.0, 0.0)
+BIOR44_DEC_LO = (0.0, 0.03782845550726404, -0.023849465019556843, -0.11062440441843718, 0.37740285561283066,
+                 0.8526986790088938, 0.37740285561283066, -0.11062440441843718, -0.023849465019556843, 0.03782845550726404)
+BIOR44_REC_LO = (0.0, -0.06453888262869706, -0.04068941760916406, 0.41809227322161724, 0.7884856164055829,
+                 0.41809227322161724, -0.04068941760916406, -0.06453888262869706, 0.0, 0.0)
+BIOR44_REC_HI = (0.0, -0.03782845550726404, -0.023849465019556843, 0.11062440441843718, 0.37740285561283066,
+                 -0.8526986790088938, 0.37740285561283066, 0.11062440441843718, -0.023849465019556843, -0.03782845550726404)
+
+
+def nle_mad_np(y: np.ndarray) -> np.ndarray:
+    """model/nle.py:17-27 restated in numpy: hh[a][b] = dec_hi[9-a] * dec_hi[9-b] (model/wvlt.py:34-42: outer product,
+    both axes flipped; analysis bank index 3 = high/high), cross-correlation with stride 2 and no padding per channel,
+    LOWER median of the magnitudes per sample (torch.median), / 0.6745.  y (N,C,H,W) -> (N,) float32."""
+    y = np.asarray(y, dtype=np.float32)
+    N, C, H, W = y.shape
+    g = np.asarray(BIOR44_DEC_HI, dtype=np.float32)[::-1].copy()
+    hh = (g[:, None] * g[None, :]).astype(np.float32)
+    Ho, Wo = (H - 10) // 2 + 1, (W - 10) // 2 + 1
+    acc = np.zeros((N, C, Ho, Wo), dtype=np.float32)
+    for a in range(10):
+        for b in range(10):
+            if hh[a, b] != 0.0:
+                acc += y[:, :, a:a + 2 * Ho - 1:2, b:b + 2 * Wo - 1:2] * hh[a, b]
+    mag = np.abs(acc).reshape(N, -1)
+    k = (mag.shape[1] - 1) // 2
+    med = np.partition(mag, k, axis=1)[:, k]
+    return (med / np.float32(0.6745)).astype(np.float32)

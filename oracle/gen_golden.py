@@ -107,8 +107,35 @@ def tc2_cases(ref):
     _dump("gdlnet_s1_c3", net, torch.rand(1, 3, 24, 40, generator=g), 15.0, None, gabor=True, trace=False)
 
 
+def nle_cases():
+    """model/nle.py nle_mad of the unmodified reference (pywt stubbed with the baked bior4.4 table):  python oracle/gen_golden.py nle"""
+    import cdl_oracle as O
+    nle = _refshim.load_nle((O.BIOR44_DEC_LO, O.BIOR44_DEC_HI, O.BIOR44_REC_LO, O.BIOR44_REC_HI))
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for i, (shape, sig) in enumerate([((2, 1, 64, 80), (25.0, 10.0)), ((1, 3, 33, 47), (15.0,)), ((3, 2, 10, 11), (5.0, 50.0, 1.0)),
+                                      ((1, 1, 128, 128), (25.0,))]):
+        yy, xx = torch.meshgrid(torch.arange(shape[-2]) / 9.0, torch.arange(shape[-1]) / 7.0, indexing="ij")
+        clean = 0.5 + 0.25 * torch.sin(xx) * torch.cos(yy) + torch.zeros(*shape)                    # smooth: the HH band is all noise
+        if i == 1:
+            clean = clean + 0.2 * torch.rand(*shape, generator=g)                                  # textured: the estimate is biased up
+        s = torch.tensor(sig).reshape(-1, 1, 1, 1) / 255.0
+        y = clean + s * torch.randn(*shape, generator=g)
+        with torch.no_grad():
+            sh = nle.noise_level(y, method="MAD")
+        assert tuple(sh.shape) == (shape[0], 1, 1, 1)
+        out[f"y{i}"] = y.numpy()
+        out[f"sigma_hat{i}"] = sh.reshape(-1).numpy()
+        out[f"sigma_true{i}"] = s.reshape(-1).numpy()
+    np.savez_compressed(os.path.join(OUT, "nle_mad.npz"), n=np.int64(4), **out)
+    print("wrote nle_mad.npz", {k: v.shape for k, v in out.items() if k.startswith("sigma_hat")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["nle"]:
+        nle_cases()
+        sys.exit(0)
     ref = _refshim.load()
     if sys.argv[1:] == ["tc2"]:
         tc2_cases(ref)
