@@ -16,8 +16,8 @@
 #include "cdl_prepost.cuh"
 #include "cdl_tc_analysis.cuh"
 #include "cdl_tc_synthesis.cuh"
-#include "cdl_tc_synthesis_h.cuh"
 #include "cdl_nle.cuh"
+#include "cdl_input.cuh"
 #include "cdl_tc2_analysis.cuh"
 #include "cdl_tc2_analysis_x3.cuh"
 #include "cdl_tc2_synthesis.cuh"
@@ -126,8 +126,6 @@ struct cdl_plan {
   size_t wA_layer, wB_layer;
   // tcgen05 path (3D, P = 7^3, s = 2, C = 1)
   bool tc_ana, tc_syn;
-  bool syn_h;          // synthesis kernel form: tap half per CTA with double-buffered accumulators (cdl_tc_synthesis_h.cuh; default) or
-                       // the cta_group::2 pair form (cdl_tc_synthesis.cuh; CDL_SYN_H=0)
   float* wAtc;         // [K][2 ranks][43][88*8] tf32 filters in UMMA layout
   float* wBtc;         // [K][2 ranks][176*176]
   float* wBtc_lo;      // layer 0 only: tf32(W - tf32(W)), for the 3-term final synthesis
@@ -311,7 +309,6 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   memset(p, 0, sizeof(*p));
   p->desc = *d;
   p->dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
-  p->syn_h = getenv("CDL_SYN_H") ? atoi(getenv("CDL_SYN_H")) != 0 : true;
   const int s = d->s;
   const bool slab = d->halo_front || d->halo_back;
 
@@ -452,8 +449,6 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
         (e = cudaMalloc(&p->wBtc_lo, p->wBtc_layer * sizeof(float))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_synthesis<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSynSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute((const void*)tc::h::k_tc_synthesis_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::h::kSmemBytesH)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute((const void*)tc::h::k_tc_synthesis_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::h::kSmemBytesH)) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc::k_tc_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kAnaSmemBytes)) != cudaSuccess) {
       cdl_plan_destroy(p);
       return CDL_CUDA_ERROR_BASE + (int)e;
@@ -631,12 +626,10 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
     if (p->tc_ana) {
       tc::k_pack_tc_analysis<<<64, 256, 0, st>>>(A[k], p->wAtc + (size_t)k * p->wAtc_layer, g.M);
       CDL_LAUNCH_CHECK(p);
-      if (p->syn_h) tc::h::k_pack_tc_synthesis_h<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M, 0);
-      else tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M, 0);
+      tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[k], p->wBtc + (size_t)k * p->wBtc_layer, g.M, 0);
       CDL_LAUNCH_CHECK(p);
       if (k == 0) {
-        if (p->syn_h) tc::h::k_pack_tc_synthesis_h<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
-        else tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
+        tc::k_pack_tc_synthesis<<<64, 256, 0, st>>>(B[0], p->wBtc_lo, g.M, 1);
         CDL_LAUNCH_CHECK(p);
       }
     }
@@ -709,6 +702,37 @@ extern "C" int cdl_preprocess(cdl_plan_t* p, const float* y, const float* mask, 
   rc = cdl_mean_from_sums(p, sums, mean, stream_);
   if (rc) return rc;
   return cdl_center_pad(p, y, mask, mean, yp, mask_p, stream_);
+}
+
+// awgn + mask + pre_process in two passes over the clean clip (cdl_input.cuh)
+extern "C" int cdl_preprocess_noisy(cdl_plan_t* p, const float* x, const float* noise, const float* c, const float* mask, int bayer,
+                                    float* y_out, float* yp, float* mask_p, float* mean, void* ws, void* stream_) {
+  if (!p || !x || !yp || !mean) return CDL_ERR_NULL;
+  if (!ws) return CDL_ERR_WORKSPACE;
+  if (noise && !c) return CDL_ERR_NULL;
+  if (bayer && (mask || p->desc.ndim != 2 || p->g.C != 3)) return CDL_ERR_UNSUPPORTED;     // utils.gen_bayer_mask: 2-D RGB only
+  const bool masked = bayer || mask;
+  if (masked != (p->desc.has_mask != 0)) return CDL_ERR_SHAPE;                             // the plan was created with/without a mask
+  if (masked && !mask_p) return CDL_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream_;
+  PadParams q = pad_params(p);
+  NoisySrc s;
+  s.x = x; s.noise = noise; s.c = c; s.mask = mask;
+  s.mode = bayer ? kMaskBayer2D : (mask ? kMaskTensor : kMaskNone);
+  s.C = q.C; s.D = q.D; s.H = q.H; s.W = q.W;
+  const long long per = (long long)q.C * q.D * q.H * q.W;
+  double* partial = reinterpret_cast<double*>((char*)ws + p->off.partial);
+  double* sums = reinterpret_cast<double*>((char*)ws + p->off.sums);
+  k_reduce_partial_noisy<<<dim3(kRedBlocksPerSample, q.N), kRedThreads, 0, st>>>(s, y_out, partial, per);
+  CDL_LAUNCH_CHECK(p);
+  k_reduce_final<<<ceil_div(q.N, 128), 128, 0, st>>>(partial, sums, kRedBlocksPerSample, q.N, masked ? 1 : 0, (double)per);
+  CDL_LAUNCH_CHECK(p);
+  { int rc = cdl_mean_from_sums(p, sums, mean, stream_); if (rc) return rc; }
+  const long long total = (long long)q.N * q.C * q.Fd * q.Fh * q.Fw;
+  long long blocks = (total + 255) / 256; if (blocks > 148 * 16) blocks = 148 * 16;
+  k_center_pad_noisy<<<(int)blocks, 256, 0, st>>>(s, mean, yp, mask_p, q);
+  CDL_LAUNCH_CHECK(p);
+  return CDL_OK;
 }
 
 extern "C" int cdl_postprocess(cdl_plan_t* p, const float* xphat, const float* mean, float* xhat, void* stream_) {
@@ -884,27 +908,11 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.dbg = g_tc_dbg;
     a.dbg_mode = p->dbg_mode;
     const CUtensorMap* zmap;
-    { const int k4 = p->syn_h ? tc::h::kChK4 : tc::kSChunkK4;      // box = one A-ring slot of the kernel form in use
-      int rc = cached_tmap(p, z, -k4, [&](CUtensorMap* m) { return make_code_tmap(m, z, p->g, k4); }, &zmap); if (rc) return rc; }
+    { int rc = cached_tmap(p, z, -1, [&](CUtensorMap* m) { return make_code_tmap(m, z, p->g); }, &zmap); if (rc) return rc; }
     const bool dz3 = !residual && k == 0;
     // Final dictionary synthesis xphat = D z (model/net.py:90,210): its tf32 rounding lands directly on xhat and
     // dominates the output error (measured: 7e-5 of 8e-5), so the two dropped cross terms are added back:
     //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)       (the scatter-add accumulates the three launches)
-    if (p->syn_h) {
-      long long pairs = p->sm_count / 2;
-      if (pairs > a.ntiles) pairs = a.ntiles;                      // both CTAs of a pair sweep the pair's whole tile range
-      const int grid = 2 * (int)pairs;
-      tc::h::k_tc_synthesis_h<false><<<grid, tc::h::kThreadsH, tc::h::kSmemBytesH, st>>>(a, *zmap);
-      CDL_LAUNCH_CHECK(p);
-      if (dz3) {
-        tc::h::k_tc_synthesis_h<true><<<grid, tc::h::kThreadsH, tc::h::kSmemBytesH, st>>>(a, *zmap);
-        CDL_LAUNCH_CHECK(p);
-        a.wpack = p->wBtc_lo;
-        tc::h::k_tc_synthesis_h<false><<<grid, tc::h::kThreadsH, tc::h::kSmemBytesH, st>>>(a, *zmap);
-        CDL_LAUNCH_CHECK(p);
-      }
-      return CDL_OK;
-    }
     long long pairs = p->sm_count / 2;
     if (pairs > (a.ntiles + 1) / 2) pairs = (a.ntiles + 1) / 2;
     tc::k_tc_synthesis<false><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);

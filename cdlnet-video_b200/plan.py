@@ -182,6 +182,18 @@ class Plan:
                                            _ptr(self.workspace("step")), _stream()), "cdl_preprocess")
         return yp, mp, mean
 
+    def preprocess_noisy(self, x, noise=None, c=None, mask=None, bayer=False, want_y=False):
+        """awgn + mask + pre_process fused (cdl_preprocess_noisy; reference utils.py:13-55 + model/utils.py:5-22,70-87):
+        x clean (device), noise = the caller's randn_like draw, c = sigma/255 per sample -> (yp, mask_p, mean[, noisy])"""
+        yp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device)
+        mp = torch.empty(self.fine_shape, dtype=torch.float32, device=self.device) if self.has_mask else None
+        mean = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        y = torch.empty_like(x) if want_y else None
+        _lib.check(self.lib.cdl_preprocess_noisy(self.handle, _ptr(x), _ptr(noise), _ptr(c), _ptr(mask), 1 if bayer else 0, _ptr(y),
+                                                 _ptr(yp), _ptr(mp), _ptr(mean), _ptr(self.workspace("step")), _stream()),
+                   "cdl_preprocess_noisy")
+        return (yp, mp, mean, y) if want_y else (yp, mp, mean)
+
     def reduce_sums(self, y, mask=None):
         sums = torch.empty(2 * self.N, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.cdl_reduce_sums(self.handle, _ptr(y), _ptr(mask), _ptr(sums), _ptr(self.workspace("reduce")), _stream()),

@@ -44,3 +44,36 @@ def denoise_windows(net, clip, sigma=None, mask=1, window=16, batch=4):
         for i, (a, b) in enumerate(grp):
             out[:, :, a:b] = xhat[i * N:(i + 1) * N]
     return out
+
+
+def noisy_forward(net, x, sigma, noise=None, bayer=False, mask=None, want_noisy=False):
+    """The evaluation step of the reference's analyze loops (analyze3d.py:108-128, analyze.py) on a CLEAN device tensor:
+
+        mask  = utils.gen_bayer_mask(x) if bayer else (mask or 1)
+        noisy = mask * (x + noise * (sigma / 255))         # noise = torch.randn_like(x), the caller's draw
+        xhat, z = net(noisy, sigma, mask=mask)
+
+    with awgn + mask + pre_process fused into two passes over x (cdl_preprocess_noisy) instead of ~10; the forward itself
+    is the module's native route.  sigma: number or per-sample tensor (N).  CUDA fp32 only - there is no fallback here."""
+    if not (x.is_cuda and x.dtype == torch.float32):
+        raise RuntimeError("noisy_forward needs a CUDA fp32 tensor (the fused input pipeline has no CPU route)")
+    x = x.contiguous()
+    N = x.shape[0]
+    has_mask = bool(bayer) or torch.is_tensor(mask)
+    m = mask.to(device=x.device, dtype=torch.float32).expand_as(x).contiguous() if torch.is_tensor(mask) else None
+    c = net._c_vector(sigma, N, x.device)            # sigma / 255 rounded like the reference (None when not adaptive)
+    cn = c
+    if cn is None and noise is not None:             # non-adaptive nets still get noise at the requested level
+        cn = (sigma.to(device=x.device, dtype=torch.float32).reshape(-1) / 255.0).expand(N).contiguous() if torch.is_tensor(sigma) \
+            else torch.full((N,), float(sigma) / 255.0, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), torch.no_grad():
+        key = net._weights_key()
+        prec = net._precision_for(x, m if has_mask and m is not None else (torch.ones_like(x) if has_mask else None), c, key)
+        plan = net._plan_for(x.shape, has_mask, x.device.index, prec)
+        net._set_plan_weights(plan, key)
+        net.__dict__["_last_plan"] = plan
+        res = plan.preprocess_noisy(x, None if noise is None else noise.contiguous(), cn, m, bayer=bool(bayer), want_y=want_noisy)
+        yp, mp, mean = res[:3]
+        z, xp = plan.forward(yp, mp, c)
+        xhat = plan.postprocess(xp, mean)
+    return (xhat, z, res[3]) if want_noisy else (xhat, z)

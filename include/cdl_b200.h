@@ -170,6 +170,17 @@ int  cdl_halo_add(cdl_plan_t* plan, float* r, const float* recv_prev, const floa
 int  cdl_forward_sharded(cdl_plan_t* plan, cdl_comm_t* comm, const float* yp, const float* c, float* code, float* r,
                          void* halo_ws, void* workspace, void* stream);
 
+/* ---- input pipeline fused with pre_process.  Replaces, for a clean clip x on the device,
+ *     mask  = utils.gen_bayer_mask(x) (bayer != 0; 2-D, C = 3) | a tensor (mask != NULL) | 1        utils.py:13-27
+ *     noisy = mask * (x + noise * (sigma/255))          utils.py:29-55 awgn / awgn3d, analyze3d.py:108-114, train.py:80
+ *     yp, mean, mask_p = pre_process[_3d](noisy, s, mask)                                           model/utils.py:5-22,70-87
+ * in two passes over x (sums, then centre + pad) instead of ~10.  noise = the caller's randn_like draw (NULL: none),
+ * c[n] = sigma_n / 255; y_out (optional) receives the noisy masked clip.  The plan must have been created with
+ * has_mask = (bayer || mask).  Roundings follow the reference expression, so yp / mean equal cdl_preprocess on the
+ * materialised noisy clip bit for bit.                                                                                */
+int cdl_preprocess_noisy(cdl_plan_t* plan, const float* x, const float* noise, const float* c, const float* mask, int bayer,
+                         float* y_out, float* yp, float* mask_p, float* mean, void* workspace, void* stream);
+
 /* ---- blind noise level on the device.  Replaces model/nle.py:17-27 `nle_mad` (call sites analyze.py:
  * `255 * model.nle.noise_level(noisy, method=blind)`, analyze3d.py:118-121):
  *     sigma_hat[n] = median(|HH * y[n]|) / 0.6745,   HH = diagonal bior4.4 detail filter (model/wvlt.py:5-42), stride 2,

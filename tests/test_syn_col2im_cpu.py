@@ -145,119 +145,6 @@ def synthesize(z, w, od, Fd, nctas):
     return out
 
 
-# ---- "tap half per CTA" form (cdl_tc_synthesis_h.cuh): td-major row list, each CTA of a pair owns one half of the rows for
-# every tile of the PAIR's range, 4-frame footprint ring ----
-def pack_filters_h(w):
-    """column j of half h = filter element 175*h + j (td-major: element = (td*7 + th)*7 + tw)"""
-    M = w.shape[0]
-    flat = w.reshape(M, 343)
-    B = np.zeros((2, 176, NA))
-    for h in range(2):
-        for j in range(7 * (25 - h)):
-            B[h, j, :M] = flat[:, 175 * h + j]
-    return B
-
-
-def synthesize_h(z, w, od, Fd, npairs):
-    N, M, Qd, Qh, Qw = z.shape
-    Fh, Fw = 2 * Qh, 2 * Qw
-    PL = 4
-    code = to_code(z)
-    B = pack_filters_h(w)
-    tiles_w = -(-Qw // TILE_W)
-    nrows = N * Qd * Qh
-    T = nrows * tiles_w
-    out = np.zeros((N, Fd, Fh, Fw))
-    lanes = np.arange(32)
-    gq, i8 = lanes >> 3, lanes & 7
-    o = 16 * (gq >> 1) + 2 * i8 + (gq & 1)
-    src1, src2, srcm = [np.array([lane_of(v + d) for v in o]) for d in (1, 2, 31)]
-    m1, m2, mm = (o < 31).astype(float), (o < 30).astype(float), (o > 0).astype(float)
-    parts = {0: [(0, 7), (7, 6), (13, 6), (19, 6)], 1: [(25, 6), (31, 6), (37, 6), (43, 6)]}     # (first global row, rows)
-    for pair in range(npairs):
-        t0, t1 = T * pair // npairs, T * (pair + 1) // npairs
-        for half in range(2):
-            X = np.zeros((XRING, PL, XW))
-            S = np.zeros((XRING, PL, 4, 8))
-            for tau in range(t0, t1):
-                col, qh = divmod(tau, Qh)
-                qw0 = (col % tiles_w) * TILE_W
-                col //= tiles_w
-                qd, n = col % Qd, col // Qd
-                row = (n * Qd + qd) * Qh + qh
-                last = tau == t1 - 1 or qh == Qh - 1
-                if tau == t0 or qh == 0:
-                    assert not X.any() and not S.any()
-                A = tma_tile(code, row, (qw0 >> 4) * 2, nrows, Qw)
-                D = A @ B[half].T                                    # [128 lanes, 176 columns]
-                pbase = (2 * qh) % XRING
-                for q in range(4):
-                    for row0, nr in parts[half]:
-                        for r in range(nr):
-                            rr = row0 + r
-                            c0 = 7 * (rr - 25 * half)
-                            u = D[32 * q:32 * q + 32, c0:c0 + 7]
-                            td, th = rr // 7, rr % 7
-                            tl = td - 3 * half
-                            assert 0 <= tl < PL
-                            v = [u[:, k] for k in range(7)]
-                            x0 = v[3] + v[1][src1] * m1 + v[5][srcm] * mm
-                            x1 = v[4] + v[2][src1] * m1 + v[0][src2] * m2 + v[6][srcm] * mm
-                            n0 = v[0][src1]
-                            ps = (pbase + th) % XRING
-                            cb = 4 + 64 * q + 2 * o
-                            np.add.at(X[ps, tl], cb, x0)
-                            np.add.at(X[ps, tl], cb + 1, x1)
-                            l0, l31 = int(np.where(o == 0)[0][0]), int(np.where(o == 31)[0][0])
-                            S[ps, tl, q, 0] += v[0][l0]
-                            S[ps, tl, q, 1] += v[1][l0]
-                            S[ps, tl, q, 2] += v[2][l0] + n0[l0]
-                            S[ps, tl, q, 4] += v[5][l31]
-                            S[ps, tl, q, 5] += v[6][l31]
-                for pi in range(XRING if last else 2):
-                    pr = 2 * qh + pi
-                    for tl in range(PL):
-                        gd, gh = 2 * qd + tl + 3 * half - od, pr - 3
-                        for c4 in range(XW // 4):
-                            gw = 2 * qw0 - 4 + 4 * c4
-                            cell = X[pr % XRING, tl, 4 * c4:4 * c4 + 4].copy()
-                            X[pr % XRING, tl, 4 * c4:4 * c4 + 4] = 0
-                            if (c4 & 15) == 0 and c4 < 64:
-                                cell[1:4] += S[pr % XRING, tl, c4 >> 4, 0:3]
-                                S[pr % XRING, tl, c4 >> 4, 0:4] = 0
-                            elif (c4 & 15) == 1 and c4 >= 17:
-                                cell[0:2] += S[pr % XRING, tl, (c4 - 17) >> 4, 4:6]
-                                S[pr % XRING, tl, (c4 - 17) >> 4, 4:8] = 0
-                            if 0 <= gd < Fd and 0 <= gh < Fh and gw >= 0 and gw + 4 <= Fw:
-                                out[n, gd, gh, gw:gw + 4] += cell
-            assert not X.any() and not S.any()
-    return out
-
-
-@pytest.mark.parametrize("N,M,Qd,Qh,Qw,npairs", [(1, 5, 2, 3, 20, 3), (2, 3, 1, 4, 16, 2), (1, 4, 2, 2, 136, 4), (1, 2, 3, 5, 6, 1), (1, 2, 1, 3, 130, 5)])
-def test_half_form_equals_conv_transpose3d(N, M, Qd, Qh, Qw, npairs):
-    rng = np.random.default_rng(2)
-    z = rng.integers(-3, 4, size=(N, M, Qd, Qh, Qw)).astype(np.float64)
-    w = rng.integers(-2, 3, size=(M, 1, 7, 7, 7)).astype(np.float64)
-    ref = F.conv_transpose3d(torch.from_numpy(z), torch.from_numpy(w), stride=2, padding=3, output_padding=1)[:, 0].numpy()
-    got = synthesize_h(z, w, od=3, Fd=2 * Qd, npairs=npairs)
-    assert np.array_equal(got, ref)
-
-
-def test_half_form_chunk_slots_and_parities():
-    """A-ring bookkeeping of the half form: the MMA warp's compile-time (slot, parity) per (round, tile-in-round, chunk) equal
-    the TMA warp's running counter gc = 6*it + c -> slot gc & 3, use parity (gc >> 2) & 1."""
-    for it in range(0, 40, 2):
-        rnd = it >> 1
-        for u2 in range(2):
-            for c in range(6):
-                lc = 6 * u2 + c
-                gc = 6 * (it + u2) + c
-                assert lc & 3 == gc & 3
-                assert ((rnd + (lc >> 2)) & 1) == ((gc >> 2) & 1)
-            assert ((it + u2) >> 1) & 1 == rnd & 1                   # dfull / dempty parity of buffer u2
-
-
 @pytest.mark.parametrize("N,M,Qd,Qh,Qw,nctas", [(1, 5, 2, 3, 20, 3), (2, 3, 1, 4, 16, 5), (1, 4, 2, 2, 136, 4), (1, 2, 3, 5, 6, 2), (1, 2, 1, 3, 130, 7)])
 def test_model_equals_conv_transpose3d(N, M, Qd, Qh, Qw, nctas):
     rng = np.random.default_rng(0)
