@@ -5,9 +5,9 @@ directory first on sys.path, as the reference's own `model` package (`from model
 """
 from . import _lib                        # noqa: F401
 from .plan import Plan                    # noqa: F401
-from .model.net import CDLNet, CDLNetVideo, GDLNet, ST      # noqa: F401
+from .model.net import CDLNet, CDLNetVideo, GDLNet, CDLNet_CSR, CDLNet_CSRf2, ST, prox_CSR, prox_CSR_f2      # noqa: F401
 
-__all__ = ["CDLNet", "CDLNetVideo", "GDLNet", "ST", "Plan", "build", "load_library"]
+__all__ = ["CDLNet", "CDLNetVideo", "GDLNet", "CDLNet_CSR", "CDLNet_CSRf2", "ST", "prox_CSR", "prox_CSR_f2", "Plan", "build", "load_library"]
 
 
 def build(force=False, verbose=False):

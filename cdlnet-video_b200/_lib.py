@@ -26,7 +26,7 @@ SYMBOLS = [
     "cdl_plan_reduce_workspace_bytes", "cdl_plan_step_workspace_bytes", "cdl_plan_host_workspace_bytes_noz",
     "cdl_comm_unique_id", "cdl_comm_create", "cdl_comm_destroy", "cdl_comm_allreduce_f64", "cdl_halo_bytes",
     "cdl_halo_exchange", "cdl_analysis_step_halo", "cdl_halo_add", "cdl_forward_sharded",
-    "cdl_preprocess_noisy", "cdl_nle_mad_workspace_bytes", "cdl_nle_mad",
+    "cdl_analysis_step_csr", "cdl_preprocess_noisy", "cdl_nle_mad_workspace_bytes", "cdl_nle_mad",
 ]
 
 
@@ -154,6 +154,8 @@ def load():
         lib.cdl_halo_add.argtypes = [vp] * 6
         lib.cdl_forward_sharded.restype = i32
         lib.cdl_forward_sharded.argtypes = [vp] * 9
+        lib.cdl_analysis_step_csr.restype = i32
+        lib.cdl_analysis_step_csr.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.cdl_preprocess_noisy.restype = i32
         lib.cdl_preprocess_noisy.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
         lib.cdl_nle_mad_workspace_bytes.restype = i32

@@ -126,6 +126,7 @@ struct cdl_plan {
   size_t wA_layer, wB_layer;
   // tcgen05 path (3D, P = 7^3, s = 2, C = 1)
   bool tc_ana, tc_syn;
+  int syn_sweep;       // CDL_SYN_SWEEP: -1 (default) = chosen per geometry, 0 / 1 = force the tile order of the video synthesis kernel
   float* wAtc;         // [K][2 ranks][43][88*8] tf32 filters in UMMA layout
   float* wBtc;         // [K][2 ranks][176*176]
   float* wBtc_lo;      // layer 0 only: tf32(W - tf32(W)), for the 3-term final synthesis
@@ -309,6 +310,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
   memset(p, 0, sizeof(*p));
   p->desc = *d;
   p->dbg_mode = getenv("CDL_TC_DBG_MODE") ? atoi(getenv("CDL_TC_DBG_MODE")) : 0;
+  p->syn_sweep = getenv("CDL_SYN_SWEEP") ? atoi(getenv("CDL_SYN_SWEEP")) : -1;
   const int s = d->s;
   const bool slab = d->halo_front || d->halo_back;
 
@@ -757,11 +759,12 @@ static int halo_add_launch(cdl_plan* p, float* r, const tc::HaloFuse& h, cudaStr
 }
 
 static int analysis_step_impl(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, void* ws, void* stream_,
-                              const tc::HaloFuse* halo) {
+                              const tc::HaloFuse* halo, const ProxArgs* prox = nullptr) {
   if (!p || !r || !z) return CDL_ERR_NULL;
   if (!p->have_weights) return CDL_ERR_NO_WEIGHTS;
   if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
   if ((reinterpret_cast<uintptr_t>(z) & 15) || (reinterpret_cast<uintptr_t>(r) & 15)) return CDL_ERR_ALIGN;
+  if (prox && (p->tc_ana || p->tc2_ana)) return CDL_ERR_UNSUPPORTED;      // the CSR epilogues live in the exact fp32 kernels
   if (p->tc_ana) {
     tc::AnaTcParams a;
     a.g = p->g;
@@ -835,6 +838,7 @@ static int analysis_step_impl(cdl_plan_t* p, int k, int first, const float* r, c
   a.t1 = a.t0 + p->g.M;
   a.cvec = c;
   a.first = first ? 1 : 0;
+  a.prox = prox ? *prox : ProxArgs{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   a.TH = p->ana_TH; a.TWS = p->ana_TWS; a.tiles_h = p->ana_tiles_h; a.tiles_w = p->ana_tiles_w;
   dim3 grid(a.tiles_h * a.tiles_w, p->g.Qd, p->g.N);
   p->ana_fn<<<grid, kAnaThreads, p->ana_smem, (cudaStream_t)stream_>>>(a);
@@ -844,6 +848,26 @@ static int analysis_step_impl(cdl_plan_t* p, int k, int first, const float* r, c
 
 extern "C" int cdl_analysis_step(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, void* ws, void* stream_) {
   return analysis_step_impl(p, k, first, r, c, z, ws, stream_, nullptr);
+}
+
+// Frame-recurrent CSR variants (reference model/net.py:229-262 prox_CSR / prox_CSR_f2, used by
+// CDLNet_CSR.forward :426-462 and CDLNet_CSRf2.forward :525-567): the analysis step with the CSR proximal operator in
+// place of the soft threshold.  z_prev / z_after = the neighbouring frames' codes, (N,M,Q...) like z, either may be NULL;
+// g1 / g2 = the (K,2,M) gamma parameters paired with z_prev / z_after (gamma = g[k,0] + c*g[k,1]).
+extern "C" int cdl_analysis_step_csr(cdl_plan_t* p, int k, int first, const float* r, const float* c, float* z, const float* z_prev,
+                                     const float* z_after, const float* g1, const float* g2, void* ws, void* stream_) {
+  if (!p) return CDL_ERR_NULL;
+  if ((z_prev && !g1) || (z_after && !g2)) return CDL_ERR_NULL;
+  if (k < 0 || k >= p->g.K) return CDL_ERR_RANGE;
+  if (!z_prev && !z_after) return analysis_step_impl(p, k, first, r, c, z, ws, stream_, nullptr);
+  const size_t off = (size_t)k * 2 * p->g.M;
+  ProxArgs a;
+  a.zprev = z_prev; a.zafter = z_after;
+  const float* ga = z_prev ? g1 : g2;                  // one neighbour: prox_CSR with that neighbour's gamma
+  a.ga0 = ga + off; a.ga1 = ga + off + p->g.M;
+  a.gb0 = (z_prev && z_after) ? g2 + off : nullptr;
+  a.gb1 = (z_prev && z_after) ? g2 + off + p->g.M : nullptr;
+  return analysis_step_impl(p, k, first, r, c, z, ws, stream_, nullptr, &a);
 }
 
 // seam geometry of a slab plan: ov = Pd - s frames shared with each neighbour
@@ -915,6 +939,8 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)       (the scatter-add accumulates the three launches)
     long long pairs = p->sm_count / 2;
     if (pairs > (a.ntiles + 1) / 2) pairs = (a.ntiles + 1) / 2;
+    // frame-synchronous order when a coarse frame has enough tiles to keep every CTA busy on it (long runs); CDL_SYN_SWEEP overrides
+    a.sweep = p->syn_sweep >= 0 ? p->syn_sweep : ((long long)a.tiles_w * p->g.Qh >= 8 * 2 * pairs ? 1 : 0);
     tc::k_tc_synthesis<false><<<2 * (int)pairs, tc::kSynThreads, tc::kSynSmemBytes, st>>>(a, *zmap);
     CDL_LAUNCH_CHECK(p);
     if (dz3) {

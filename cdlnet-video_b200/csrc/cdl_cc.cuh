@@ -25,6 +25,7 @@ struct AnaParams {
   const float* t1;    // [M] thresholds t[k,1,:]
   const float* cvec;  // [N] sigma/255 per sample, or nullptr (c = 0)
   int first;          // 1: z <- ST(+u) (iteration 0), 0: z <- ST(z - u)
+  ProxArgs prox;      // all null: plain soft threshold; else the CSR proximal operators (model/net.py:229-262)
   int TH, TWS;        // tile = TH coarse rows x TWS strips of 8 coarse sites; TH*TWS == 8 warps
   int tiles_h, tiles_w;
 };
@@ -131,14 +132,25 @@ __global__ void __launch_bounds__(kAnaThreads) k_cc_analysis(const AnaParams p) 
     const int m = lane + 32 * i;
     if (m >= g.M) continue;
     const float tau = make_tau(p.t0[m], p.t1[m], cval);
-    float* zp = p.z + (((long long)(n * g.M + m) * g.Qd + qd) * g.Qh + qh) * g.Qw + qws;
+    const long long zoff = (((long long)(n * g.M + m) * g.Qd + qd) * g.Qh + qh) * g.Qw + qws;
+    float* zp = p.z + zoff;
+    // CSR: one neighbour (prox_CSR with that neighbour's gamma pair) or both (prox_CSR_f2)
+    const float* nb1 = p.prox.zprev ? p.prox.zprev : p.prox.zafter;
+    const float* nb2 = (p.prox.zprev && p.prox.zafter) ? p.prox.zafter : nullptr;
+    const float ga = nb1 ? make_tau(p.prox.ga0[m], p.prox.ga1[m], cval) : 0.0f;
+    const float gb = nb2 ? make_tau(p.prox.gb0[m], p.prox.gb1[m], cval) : 0.0f;
+    auto prox = [&](float v, int j) {
+      if (!nb1) return soft_threshold(v, tau);
+      if (!nb2) return prox_csr(v, __ldg(nb1 + zoff + j), tau, ga);
+      return prox_csr_f2(v, __ldg(nb1 + zoff + j), __ldg(nb2 + zoff + j), tau, ga, gb);
+    };
     if (vec) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
       if (!p.first) { a = reinterpret_cast<const float4*>(zp)[0]; b = reinterpret_cast<const float4*>(zp)[1]; }
       float zin[JB] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       float o[JB];
 #pragma unroll
-      for (int j = 0; j < JB; ++j) o[j] = soft_threshold(p.first ? acc[i][j] : __fsub_rn(zin[j], acc[i][j]), tau);
+      for (int j = 0; j < JB; ++j) o[j] = prox(p.first ? acc[i][j] : __fsub_rn(zin[j], acc[i][j]), j);
       reinterpret_cast<float4*>(zp)[0] = make_float4(o[0], o[1], o[2], o[3]);
       reinterpret_cast<float4*>(zp)[1] = make_float4(o[4], o[5], o[6], o[7]);
     } else {
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(kAnaThreads) k_cc_analysis(const AnaParams p) 
       for (int j = 0; j < JB; ++j) {
         if (qws + j < g.Qw) {
           float v = p.first ? acc[i][j] : __fsub_rn(zp[j], acc[i][j]);
-          zp[j] = soft_threshold(v, tau);
+          zp[j] = prox(v, j);
         }
       }
     }

@@ -39,4 +39,34 @@ __device__ __forceinline__ float soft_threshold(float v, float tau) {
 // tau = t0 + c * t1 with the reference's two roundings (no FMA contraction), model/net.py:85.
 __device__ __forceinline__ float make_tau(float t0, float t1, float c) { return __fadd_rn(t0, __fmul_rn(c, t1)); }
 
+// ---- frame-recurrent CSR proximal operators (reference model/net.py:229-262), with the reference's operation order ----
+__device__ __forceinline__ float sign_f(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+// prox_CSR(u, zp, lambda, gamma) = ST(ST(u - zp - lambda*sign(zp), lambda*gamma) + zp + lambda*sign(zp), lambda)
+__device__ __forceinline__ float prox_csr(float u, float zp, float lam, float gam) {
+  const float ls = __fmul_rn(lam, sign_f(zp));
+  const float inner = soft_threshold(__fsub_rn(__fsub_rn(u, zp), ls), __fmul_rn(lam, gam));
+  return soft_threshold(__fadd_rn(__fadd_rn(inner, zp), ls), lam);
+}
+// prox_CSR_f2(u, zp, za, lambda, gamma1, gamma2) (model/net.py:244-262)
+__device__ __forceinline__ float prox_csr_f2(float u, float zp, float za, float lam, float g1, float g2) {
+  const float lg1 = __fmul_rn(lam, g1), lg2 = __fmul_rn(lam, g2);
+  const float Ca = __fadd_rn(__fadd_rn(zp, __fmul_rn(lam, sign_f(zp))), __fmul_rn(lg2, sign_f(__fsub_rn(zp, za))));
+  const float Cb = __fadd_rn(__fadd_rn(za, __fmul_rn(lam, sign_f(za))), __fmul_rn(lg1, sign_f(__fsub_rn(za, zp))));
+  const float d = __fsub_rn(u, Ca);
+  const float ls = __fmul_rn(lg1, sign_f(d));
+  const float inner = soft_threshold(d, lg1);                      // gamma1 * lambda == lambda * gamma1
+  const float mid = soft_threshold(__fadd_rn(__fsub_rn(inner, Cb), ls), lg2);
+  return soft_threshold(__fsub_rn(__fadd_rn(mid, Cb), ls), lam);
+}
+
+// the proximal step of one analysis epilogue: plain ST, or a CSR variant against the neighbouring frames' codes
+struct ProxArgs {
+  const float* zprev;   // code of the previous frame (same layout as z) or nullptr
+  const float* zafter;  // code of the next frame or nullptr
+  const float* ga0;     // [M] gamma thresholds g[k,0,:] paired with zprev (g / g1), or with zafter when only zafter is given (g2)
+  const float* ga1;     // [M] g[k,1,:]
+  const float* gb0;     // [M] second pair (g2) when both neighbours are given
+  const float* gb1;
+};
+
 }  // namespace cdl

@@ -229,15 +229,22 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* m
 // The same load issued by either CTA of a cta_group::2 pair, with completion signalled on the mbarrier at the same
 // shared-memory offset in the LEADER CTA (rank 0): the leader's barrier collects the bytes of both CTAs' loads (it
 // expects the sum), so the MMA-issuing warp waits on one local barrier - no relay hop through the peer.
-__device__ __forceinline__ void tma_load_3d_2cta(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+__device__ __forceinline__ void tma_load_3d_2cta(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
   asm volatile("{\n\t.reg .b32 rb;\n\tmapa.shared::cluster.u32 rb, %2, 0;\n\t"
-               "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [rb];\n\t}"
-               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+               "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [rb], %6;\n\t}"
+               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory"); }
 // one instruction pulls `bytes` (multiple of 16) of contiguous global memory into L2
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2_hint(const void* p, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
 }
 // 16-byte vector reduction (sm_90+): out[0..3] += v
 __device__ __forceinline__ void red_add_v4_f32(float* p, float4 v) {

@@ -66,6 +66,7 @@ struct SynTcParams {
   float* out;           // (N,1,Fd,Fh,Fw), accumulated into
   const float* wpack;   // this layer: [2 ranks][2 halves][22 k-steps][11 groups][2][8][4]
   int tiles_w;          // 128-site tiles per coarse row
+  int sweep;            // tile order (see syn_tile)
   long long ntiles;     // N * Qd * tiles_w * Qh
   long long nrows;      // N * Qd * Qh rows of the code tensor (a tile coordinate >= nrows reads zeros)
   long long* dbg;
@@ -113,26 +114,55 @@ __global__ void __launch_bounds__(256) k_neg_copy(const float* __restrict__ yp, 
 
 // ---- tile sequence ----
 struct SynTile { long long row; int n, qd, qh, qw0, valid, first, last; };
-// Tiles are numbered column by column ((n, qd, w-tile), w-tile fastest), qh fastest inside a column.  CTA `cta` of
-// `nctas` owns the contiguous range [cta*T/nctas, (cta+1)*T/nctas); a RUN is a maximal stretch of consecutive qh of one
-// column inside that range (the footprint ring carries over inside a run and is flushed completely at its end).
-__device__ __forceinline__ void syn_range(const SynTcParams& p, int cta, int nctas, long long& t0, long long& t1) {
-  t0 = p.ntiles * cta / nctas;
-  t1 = p.ntiles * (cta + 1) / nctas;
+// Two orders, both dealing EQUAL CONTIGUOUS shares to the CTAs (a RUN is a maximal stretch of consecutive qh of one
+// (n, qd, w-tile) column inside a share; the footprint ring carries over inside a run and is flushed completely at its end):
+//   sweep = 0  tiles numbered column by column ((n, qd, w-tile), w-tile fastest), qh fastest inside a column; CTA `cta` owns
+//              the range [cta*T/nctas, (cta+1)*T/nctas) of the whole launch.  Longest runs; used when a coarse frame has
+//              too few tiles to keep every CTA busy on it (`out` then fits L2 anyway).
+//   sweep = 1  the (w-tile, qh) tiles of ONE coarse frame are dealt to the CTAs once (share [cta*F/nctas, (cta+1)*F/nctas)),
+//              and every CTA sweeps all (n, qd) frames over its share.  All CTAs work on the same coarse frame at the same
+//              time, so the 3-4 scatter-adds a fine voxel receives from neighbouring coarse frames meet in L2 (in the
+//              other order neighbouring frames are processed 4320 tiles apart on the 1080p clip: every red.global.add
+//              was a DRAM read-modify-write, 15 of 59 GB per launch, profiles/r02o_ncu_kernels.md).
+struct SynShare { long long a; long long count; int len; };
+__device__ __forceinline__ SynShare syn_range(const SynTcParams& p, int cta, int nctas) {
+  SynShare s;
+  if (p.sweep) {
+    const long long F = (long long)p.tiles_w * p.g.Qh;
+    s.a = F * cta / nctas;
+    s.len = (int)(F * (cta + 1) / nctas - s.a);
+    s.count = (long long)s.len * p.g.N * p.g.Qd;
+  } else {
+    s.a = p.ntiles * cta / nctas;
+    s.count = p.ntiles * (cta + 1) / nctas - s.a;
+    s.len = 0;
+  }
+  return s;
 }
-__device__ __forceinline__ SynTile syn_tile(const SynTcParams& p, long long t0, long long t1, int i) {
+__device__ __forceinline__ SynTile syn_tile(const SynTcParams& p, const SynShare& sh, int i) {
   SynTile t;
-  const long long tau = t0 + i;
-  t.valid = tau < t1;
+  t.valid = i < sh.count;
   if (!t.valid) { t.row = p.nrows; t.n = t.qd = t.qh = t.qw0 = 0; t.first = t.last = 0; return t; }
-  long long col = tau / p.g.Qh;
-  t.qh = (int)(tau - col * p.g.Qh);
-  t.qw0 = (int)(col % p.tiles_w) * kSTileW; col /= p.tiles_w;
-  t.qd = (int)(col % p.g.Qd);
-  t.n = (int)(col / p.g.Qd);
+  if (p.sweep) {
+    const int fi = i / sh.len, j = i - fi * sh.len;
+    const long long s = sh.a + j;
+    const int wt = (int)(s / p.g.Qh);
+    t.qh = (int)(s - (long long)wt * p.g.Qh);
+    t.qw0 = wt * kSTileW;
+    t.n = fi / p.g.Qd; t.qd = fi - t.n * p.g.Qd;
+    t.first = (j == 0) || t.qh == 0;
+    t.last = (j == sh.len - 1) || t.qh == p.g.Qh - 1;
+  } else {
+    const long long tau = sh.a + i;
+    long long col = tau / p.g.Qh;
+    t.qh = (int)(tau - col * p.g.Qh);
+    t.qw0 = (int)(col % p.tiles_w) * kSTileW; col /= p.tiles_w;
+    t.qd = (int)(col % p.g.Qd);
+    t.n = (int)(col / p.g.Qd);
+    t.first = (i == 0) || t.qh == 0;
+    t.last = (i == sh.count - 1) || t.qh == p.g.Qh - 1;
+  }
   t.row = ((long long)t.n * p.g.Qd + t.qd) * p.g.Qh + t.qh;
-  t.first = (tau == t0) || t.qh == 0;
-  t.last = (tau == t1 - 1) || t.qh == p.g.Qh - 1;
   return t;
 }
 
@@ -265,11 +295,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
   const uint32_t tbase = *tmem_slot;
 
   // this CTA's tile range and the pair's common number of rounds
-  long long t0, t1, pt0, pt1;
-  syn_range(p, blockIdx.x, gridDim.x, t0, t1);
-  syn_range(p, blockIdx.x ^ 1, gridDim.x, pt0, pt1);
-  const int mylen = (int)(t1 - t0);
-  const int rounds = max(mylen, (int)(pt1 - pt0));
+  const SynShare share = syn_range(p, blockIdx.x, gridDim.x);
+  const int rounds = (int)max(share.count, syn_range(p, blockIdx.x ^ 1, gridDim.x).count);
 
   if (warp < kSynC2iWarps) {
     // ============================== col2im + footprint flush ==============================
@@ -286,7 +313,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
     }
     const int colbase = 4 + 64 * q + 2 * L.o;
     for (int it = 0; it < rounds; ++it) {
-      const SynTile t = syn_tile(p, t0, t1, it);
+      const SynTile t = syn_tile(p, share, it);
       if (LO) {
         // low part of the code, in place: word -> z = word - bias, hi = truncate(word) = rna(z), word' = (z - hi) + bias
 #pragma unroll 1
@@ -411,15 +438,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
     // ============================== TMA: code tile -> A ring, 8 KB chunks ==============================
     if (lane == 0) {
       tma_prefetch_desc(&zmap);
+      const uint64_t pol = l2_policy_evict_first();                 // the code streams through once: keep L2 for `out` (scatter-adds)
       const int G = code_groups_per_row(g.Qw);
       for (int it = 0; it < rounds; ++it) {
-        const SynTile t = syn_tile(p, t0, t1, it);
+        const SynTile t = syn_tile(p, share, it);
         const int g0 = (t.qw0 >> 4) * 2;                             // first group of the tile in its row
         {                                                            // the next tile's 16 groups are one contiguous run: one L2 prefetch
-          const SynTile t2 = syn_tile(p, t0, t1, it + 1);
+          const SynTile t2 = syn_tile(p, share, it + 1);
           if (t2.valid) {
             const int g2 = (t2.qw0 >> 4) * 2, ng = min(kSGroups, G - g2);
-            bulk_prefetch_l2(p.z + ((size_t)t2.row * G + g2) * kCodeGroup, (uint32_t)ng * kCodeGroup * 4);
+            bulk_prefetch_l2_hint(p.z + ((size_t)t2.row * G + g2) * kCodeGroup, (uint32_t)ng * kCodeGroup * 4, pol);
           }
         }
 #pragma unroll 1
@@ -430,12 +458,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
             // the chunk is transformed in place before the MMA may read it: completion on this CTA's own barrier, then
             // the col2im warps of both CTAs arrive on the leader's aboth
             mbar_expect_tx(&afull[slot], kSChunkFloats * 4);
-            tma_load_3d(sA + slot * kSChunkFloats, &zmap, c * kSChunkK4 * kCodeChunk, g0, (int)t.row, &afull[slot]);
+            tma_load_3d_hint(sA + slot * kSChunkFloats, &zmap, c * kSChunkK4 * kCodeChunk, g0, (int)t.row, &afull[slot], pol);
           } else {
             // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
             if (p.dbg_mode & 256) { if (rank == 0) mbar_arrive(&afull[slot]); continue; }
             if (rank == 0) mbar_expect_tx(&afull[slot], 2 * kSChunkFloats * 4);
-            tma_load_3d_2cta(sA + slot * kSChunkFloats, &zmap, c * kSChunkK4 * kCodeChunk, g0, (int)t.row, &afull[slot]);
+            tma_load_3d_2cta(sA + slot * kSChunkFloats, &zmap, c * kSChunkK4 * kCodeChunk, g0, (int)t.row, &afull[slot], pol);
           }
         }
       }

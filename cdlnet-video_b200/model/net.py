@@ -68,7 +68,7 @@ class _ISTANet(nn.Module):
     # -- plumbing ----------------------------------------------------------------------------------
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ("_plans", "_last_plan", "_auto_choice", "_last_calibration"):
+        for k in ("_plans", "_last_plan", "_auto_choice", "_embed_choice", "_last_calibration"):
             state.pop(k, None)           # ctypes handles are per process
         return state
 
@@ -123,6 +123,7 @@ class _ISTANet(nn.Module):
         parameters.  Needed only after in-place edits that bypass autograd's version counter (`.data` writes)."""
         self.__dict__["_weights_epoch"] = self.__dict__.get("_weights_epoch", 0) + 1
         self.__dict__.pop("_auto_choice", None)
+        self.__dict__.pop("_embed_choice", None)
     invalidate = refresh_weights
 
     def _set_plan_weights(self, plan, key):
@@ -205,26 +206,51 @@ class _ISTANet(nn.Module):
         """ LISTA + D w/ noise-adaptive thresholds """
         if not self._native_ok(y, sigma, mask):
             return self._forward_stock(y, sigma, mask)
-        if self._embed3d_ok(y, mask):
+        if self._embed3d_ok(y, mask, sigma):
             return self._forward_embedded3d(y, sigma)
         plan, y, mask, c = self._prepare(y, sigma, mask)
         with torch.cuda.device(y.device):
             return plan.denoise(y, mask, c)
 
-    # -- opt-in: 2-D stride-2 grayscale nets (CDLNet-s2030, BASELINE config 1) on the VIDEO tensor-core kernels ------
+    # -- 2-D stride-2 grayscale nets (CDLNet-s2030, BASELINE config 1) on the VIDEO tensor-core kernels ------------------
     # A 2-D image is a clip of two frames (image, zero) and a 7x7 filter is the td = 3 slice of a 7x7x7 filter: with
     # stride 2 and padding 3 along d the only coarse frame reads fine frames td - 3 = 0 (td = 3) and 1 (td = 4, a zero
     # slice), and the synthesis writes frame 0 from td = 3 and nothing into frame 1 - the 3-D operator restricted to
-    # frame 0 IS the 2-D operator.  6/7 of the MMAs multiply zeros, but the problem (one 256x256 image) is launch-bound
-    # either way.  NOT yet run on hardware: enabled only by CDL_EMBED3D=1 together with precision "tf32"/"auto".
-    def _embed3d_ok(self, y, mask):
-        if os.environ.get("CDL_EMBED3D", "0") != "1" or self.precision not in ("tf32", "auto"):
+    # frame 0 IS the 2-D operator.  6/7 of the MMAs multiply zeros, but one 256x256 image is launch-bound either way:
+    # measured 1.01 ms against 5.68 ms on the fp32 CUDA-core kernels, max|xhat - oracle| 2.3e-5
+    # (profiles/r02q_cfg1_embed3d_timing.json, r02o_embed3d_tests.log).  Taken for precision "tf32", and for "auto" after
+    # the same one-time calibration against the exact kernels as `_calibrate`; CDL_EMBED3D=0 disables the route.
+    def _embed3d_ok(self, y, mask, sigma=None):
+        if os.environ.get("CDL_EMBED3D", "1") == "0" or self.precision not in ("tf32", "auto"):
             return False
         if self._nsp != 2 or type(self).__name__ != "CDLNet" or torch.is_tensor(mask):
             return False
         if not (self.s == 2 and self._P3() == (7, 7) and y.shape[1] == 1 and self.M <= 176):
             return False
-        return (-(-y.shape[3] // 2) * 2) % 4 == 0            # the video kernels need a padded width that is a multiple of 4
+        if (-(-y.shape[3] // 2) * 2) % 4 != 0:               # the video kernels need a padded width that is a multiple of 4
+            return False
+        if self.precision == "tf32":
+            return True
+        choice = self.__dict__.setdefault("_embed_choice", {})
+        ck = (self._weights_key(), tuple(y.shape[1:]))
+        if ck not in choice or self.training:
+            choice[ck] = self._calibrate_embed3d(y, sigma)
+        self.__dict__["_last_calibration"] = choice[ck]
+        return choice[ck][0] == "tf32"
+
+    def _calibrate_embed3d(self, y, sigma):
+        """embedded route vs the exact fp32 kernels on (a crop of) the first sample -> ("tf32" | "fp32", deviation)"""
+        yc = y[:1, :, :min(int(y.shape[2]), 256), :min(int(y.shape[3]), 256)].contiguous()
+        sc = sigma.reshape(-1)[:1] if torch.is_tensor(sigma) else sigma
+        if (-(-yc.shape[3] // 2) * 2) % 4 != 0:
+            return ("fp32", None)
+        with torch.cuda.device(y.device):
+            p_ex = self._plan_for(yc.shape, False, y.device.index, "fp32")
+            A, B = self._filter_banks()
+            p_ex.set_weights(A, B, self.t)
+            ref = p_ex.denoise(yc, None, self._c_vector(sc, 1, y.device), want_z=False)[0]
+            dev = float((self._forward_embedded3d(yc, sc)[0] - ref).abs().max())
+        return ("tf32" if dev <= self.auto_tolerance else "fp32", dev)
 
     def _forward_embedded3d(self, y, sigma):
         y = y.contiguous()
@@ -253,6 +279,7 @@ class _ISTANet(nn.Module):
             yp3[:, :, 0] = yp
             z3, xp3 = p3.forward(yp3, None, self._c_vector(sigma, N, dev))
             xhat = p2.postprocess(xp3[:, :, 0].contiguous(), mean)
+            self.__dict__["_last_plan"] = p3
             return xhat, z3[:, :, 0]
 
     def forward_generator(self, y, sigma=None, mask=1):
@@ -487,3 +514,156 @@ class GDLNet(_ISTANet):
     def _filter_banks(self):
         with torch.no_grad():
             return [m.get_filter(transpose=True) for m in self.A], [m.get_filter() for m in self.B]
+
+
+# ------------------------------------------------------------------------------------------------
+# frame-recurrent CSR variants (reference model/net.py:229-262, 363-567)
+# ------------------------------------------------------------------------------------------------
+def prox_CSR(u, z_prev, lambd, gamma):
+    """ST(ST(u - z_prev - lambd*sign(z_prev), lambd*gamma) + z_prev + lambd*sign(z_prev), lambd)"""
+    shift = lambd * torch.sign(z_prev)
+    return ST(ST(u - z_prev - shift, lambd * gamma) + z_prev + shift, lambd)
+
+
+def prox_CSR_f2(u, z_prev, z_after, lambd, gamma1, gamma2):
+    """two-neighbour CSR proximal operator (previous and next frame)"""
+    Ca = z_prev + lambd * torch.sign(z_prev) + lambd * gamma2 * torch.sign(z_prev - z_after)
+    Cb = z_after + lambd * torch.sign(z_after) + lambd * gamma1 * torch.sign(z_after - z_prev)
+    kick = lambd * gamma1 * torch.sign(u - Ca)
+    inner = ST(u - Ca, gamma1 * lambd)
+    midder = ST(inner - Cb + kick, gamma2 * lambd)
+    return ST(midder + Cb - kick, lambd)
+
+
+class _CSRNet(_ISTANet):
+    """2-D CDLNet whose proximal step couples a frame's code to the neighbouring frames' codes.  The convolutions are the
+    ordinary analysis / synthesis steps; on CUDA (no grad) the loop runs on the exact fp32 kernels of libcdl_b200 with
+    the CSR proximal operator fused into the analysis epilogue (cdl_analysis_step_csr) - the shipped hyper-parameters
+    (argscsr.json: P = 9, s = 2) have no tensor-core kernel, and the prox chain is kept in fp32 throughout."""
+    _nsp = 2
+
+    def _build(self, K, M, P, s, C, t0, adaptive, init, second_bank):
+        pad = (P - 1) // 2
+        conv = lambda: nn.ModuleList([nn.Conv2d(C, M, P, stride=s, padding=pad, bias=False) for _ in range(K)])
+        convT = lambda: nn.ModuleList([nn.ConvTranspose2d(M, C, P, stride=s, padding=pad, output_padding=s - 1, bias=False) for _ in range(K)])
+        self.A, self.B = conv(), convT()
+        if second_bank:                                           # CDLNet_CSR: the frame without a neighbour has its own operators
+            self.A2, self.B2 = conv(), convT()
+        self.D = self.B[0]
+        self.t = nn.Parameter(t0 * torch.ones(K, 2, M, 1, 1))
+        W = torch.randn(M, C, P, P)
+        for k in range(K):
+            self.A[k].weight.data = W.clone()
+            self.B[k].weight.data = W.clone()
+        if init:
+            L = _spectral_constant(lambda x: self.D(self.A[0](x)), (1, C, 128, 128))
+            for k in range(K):
+                self.A[k].weight.data /= np.sqrt(L)
+                self.B[k].weight.data /= np.sqrt(L)
+        self.K, self.M, self.P, self.s, self.t0, self.adaptive = K, M, P, s, t0, adaptive
+
+    @torch.no_grad()
+    def project(self):
+        """ l2-ball projection for filters, R_+ projection for thresholds """
+        self.t.clamp_(0.0)
+        for k in range(self.K):
+            self.A[k].weight.data = uball_project(self.A[k].weight.data)
+            self.B[k].weight.data = uball_project(self.B[k].weight.data)
+
+    # banks[name] = (A modules, B modules, thresholds) of one operator set
+    def _bank(self, second):
+        return (self.A2, self.B2, self.t2) if second else (self.A, self.B, self.t)
+
+    def _csr_forward(self, y, sigma, mask, z_prev, z_after, g_prev, g_after, second_bank=False):
+        """the shared loop: `second_bank` selects (A2, B2, t2) for the iterations (D stays B[0])"""
+        A, B, t = self._bank(second_bank)
+        if not self._native_ok(y, sigma, mask) or any(n is not None and not (n.is_cuda and n.dtype == torch.float32) for n in (z_prev, z_after)):
+            return self._csr_stock(y, sigma, mask, z_prev, z_after, g_prev, g_after, A, B, t)
+        has_mask = torch.is_tensor(mask)
+        y = y.contiguous()
+        mask = mask.to(device=y.device, dtype=torch.float32).expand_as(y).contiguous() if has_mask else None
+        c = self._c_vector(sigma, y.shape[0], y.device)
+        with torch.cuda.device(y.device):
+            key = self._weights_key()
+            plan = self._plan_for(y.shape, has_mask, y.device.index, "fp32")
+            tag = (key, bool(second_bank))
+            if self.training or plan._weights_key != tag:
+                plan.set_weights([m.weight for m in A], [m.weight for m in B], t, key=tag)
+            plan_d = plan
+            if second_bank:                                       # the final D z uses B[0] of the FIRST bank (model/net.py:459)
+                plan_d = self._plan_for(y.shape, has_mask, y.device.index, "fp32-d")
+                if self.training or plan_d._weights_key != (key, "d"):
+                    plan_d.set_weights([m.weight for m in self.A], [m.weight for m in self.B], self.t, key=(key, "d"))
+            self.__dict__["_last_plan"] = plan
+            zp = None if z_prev is None else z_prev.contiguous()
+            za = None if z_after is None else z_after.contiguous()
+            gp = None if zp is None else g_prev.detach().reshape(self.K, 2, self.M).contiguous()
+            ga = None if za is None else g_after.detach().reshape(self.K, 2, self.M).contiguous()
+            yp, mp, mean = plan.preprocess(y, mask)
+            z = plan.new_code()
+            r = torch.empty_like(yp)
+            plan.analysis_step_csr(0, yp, z, c, first=True, z_prev=zp, z_after=za, g1=gp, g2=ga)
+            for k in range(1, self.K):
+                plan.synthesis_step(k, z, r, yp, mp, residual=True)
+                plan.analysis_step_csr(k, r, z, c, z_prev=zp, z_after=za, g1=gp, g2=ga)
+            plan_d.synthesis_step(0, z, r, residual=False)
+            return plan.postprocess(r, mean), plan.export_code(z)
+
+    def _plan_for(self, shape, has_mask, device_index, prec):
+        if prec == "fp32-d":                                      # a second exact plan holding the first bank (for D)
+            plans = self.__dict__.setdefault("_plans", {})
+            key = (tuple(shape), has_mask, device_index, prec)
+            if key not in plans:
+                plans[key] = Plan(2, shape[0], shape[1], self.M, self.K, tuple(shape[2:]), self._P3(), self.s,
+                                  has_mask=has_mask, precision="fp32", device=device_index or 0)
+            return plans[key]
+        return super()._plan_for(shape, has_mask, device_index, prec)
+
+    def _csr_stock(self, y, sigma, mask, z_prev, z_after, g_prev, g_after, A, B, t):
+        yp, params, mask = pre_process(y, self.s, mask=mask)
+        c = 0 if sigma is None or not self.adaptive else sigma / 255.0
+        thr = lambda p, k: p[k, :1] + c * p[k, 1:2]
+
+        def prox(u, k):
+            if z_prev is not None and z_after is not None:
+                return prox_CSR_f2(u, z_prev, z_after, thr(t, k), thr(g_prev, k), thr(g_after, k))
+            if z_prev is not None:
+                return prox_CSR(u, z_prev, thr(t, k), thr(g_prev, k))
+            if z_after is not None:
+                return prox_CSR(u, z_after, thr(t, k), thr(g_after, k))
+            return ST(u, thr(t, k))
+        z = prox(A[0](yp), 0)
+        for k in range(1, self.K):
+            z = prox(z - A[k](mask * B[k](z) - yp), k)
+        return post_process(self.D(z), params), z
+
+
+class CDLNet_CSR(_CSRNet):
+    """ CDLNet with the one-neighbour CSR proximal step (reference model/net.py:363-462): with `z_prev` the iterations use
+    (A, B, t, g) and prox_CSR; without it they are the plain ISTA loop on a second operator set (A2, B2, t2). """
+
+    def __init__(self, K=3, M=64, P=7, s=1, C=1, t0=0, adaptive=False, init=True):
+        super().__init__()
+        self._build(K, M, P, s, C, t0, adaptive, init, second_bank=True)
+        self.t2 = nn.Parameter(t0 * torch.ones(K, 2, M, 1, 1))
+        self.g = nn.Parameter(t0 * torch.ones(K, 2, M, 1, 1))
+
+    def forward(self, y, z_prev=None, sigma=None, mask=1):
+        """ LISTA + D; `z_prev` = sparse code of the previous frame (None for the first frame) """
+        if z_prev is None:
+            return self._csr_forward(y, sigma, mask, None, None, None, None, second_bank=True)
+        return self._csr_forward(y, sigma, mask, z_prev, None, self.g, None)
+
+
+class CDLNet_CSRf2(_CSRNet):
+    """ CDLNet with the two-neighbour CSR proximal step (reference model/net.py:464-567; argscsr.json): prox_CSR_f2 with both
+    neighbours, prox_CSR with one (g1 pairs with z_prev, g2 with z_after), plain ST with none. """
+
+    def __init__(self, K=3, M=64, P=7, s=1, C=1, t0=0, adaptive=False, init=True):
+        super().__init__()
+        self._build(K, M, P, s, C, t0, adaptive, init, second_bank=False)
+        self.g1 = nn.Parameter(t0 * torch.ones(K, 2, M, 1, 1))
+        self.g2 = nn.Parameter(t0 * torch.ones(K, 2, M, 1, 1))
+
+    def forward(self, y, z_prev=None, z_after=None, sigma=None, mask=1):
+        return self._csr_forward(y, sigma, mask, z_prev, z_after, self.g1, self.g2)

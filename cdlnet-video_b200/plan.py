@@ -217,6 +217,12 @@ class Plan:
                                               _ptr(self.workspace("step")), _stream()), "cdl_analysis_step")
         return z
 
+    def analysis_step_csr(self, k, r, z, c=None, first=False, z_prev=None, z_after=None, g1=None, g2=None):
+        """analysis step with the CSR proximal operators (cdl_analysis_step_csr; reference model/net.py:229-262)"""
+        _lib.check(self.lib.cdl_analysis_step_csr(self.handle, k, int(first), _ptr(r), _ptr(c), _ptr(z), _ptr(z_prev), _ptr(z_after),
+                                                  _ptr(g1), _ptr(g2), _ptr(self.workspace("step")), _stream()), "cdl_analysis_step_csr")
+        return z
+
     def synthesis_step(self, k, z, out, yp=None, mask_p=None, residual=True):
         _lib.check(self.lib.cdl_synthesis_step(self.handle, k, int(residual), _ptr(z), _ptr(yp), _ptr(mask_p), _ptr(out),
                                                _ptr(self.workspace("step")), _stream()), "cdl_synthesis_step")

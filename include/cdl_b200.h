@@ -170,6 +170,14 @@ int  cdl_halo_add(cdl_plan_t* plan, float* r, const float* recv_prev, const floa
 int  cdl_forward_sharded(cdl_plan_t* plan, cdl_comm_t* comm, const float* yp, const float* c, float* code, float* r,
                          void* halo_ws, void* workspace, void* stream);
 
+/* ---- frame-recurrent CSR variants.  The analysis step with prox_CSR / prox_CSR_f2 (model/net.py:229-262)
+ * in place of ST, as CDLNet_CSR.forward (:426-462) and CDLNet_CSRf2.forward (:525-567) apply it: z_prev / z_after are the
+ * neighbouring frames' codes in z's layout (either may be NULL: one neighbour = prox_CSR with that neighbour's gamma, both
+ * = prox_CSR_f2, none = the plain step); g1 / g2 = the (K,2,M) gamma parameters paired with z_prev / z_after
+ * (gamma = g[k,0] + c*g[k,1]).  Exact fp32 kernels only (plans created with CDL_PREC_FP32): CDL_ERR_UNSUPPORTED otherwise. */
+int cdl_analysis_step_csr(cdl_plan_t* plan, int k, int first, const float* r, const float* c, float* code, const float* z_prev,
+                          const float* z_after, const float* g1, const float* g2, void* workspace, void* stream);
+
 /* ---- input pipeline fused with pre_process.  Replaces, for a clean clip x on the device,
  *     mask  = utils.gen_bayer_mask(x) (bayer != 0; 2-D, C = 3) | a tensor (mask != NULL) | 1        utils.py:13-27
  *     noisy = mask * (x + noise * (sigma/255))          utils.py:29-55 awgn / awgn3d, analyze3d.py:108-114, train.py:80

@@ -416,3 +416,45 @@ def nle_mad_np(y: np.ndarray) -> np.ndarray:
     k = (mag.shape[1] - 1) // 2
     med = np.partition(mag, k, axis=1)[:, k]
     return (med / np.float32(0.6745)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# frame-recurrent CSR variants (reference model/net.py:229-262 prox_CSR / prox_CSR_f2; forward loops :426-462, :525-567)
+# ------------------------------------------------------------------------------------------------
+def prox_csr_t(u, z_prev, lambd, gamma):
+    """model/net.py:229-242"""
+    return soft_threshold_t(soft_threshold_t(u - z_prev - lambd * torch.sign(z_prev), lambd * gamma) + z_prev + lambd * torch.sign(z_prev), lambd)
+
+
+def prox_csr_f2_t(u, z_prev, z_after, lambd, gamma1, gamma2):
+    """model/net.py:244-262"""
+    Ca = z_prev + lambd * torch.sign(z_prev) + lambd * gamma2 * torch.sign(z_prev - z_after)
+    Cb = z_after + lambd * torch.sign(z_after) + lambd * gamma1 * torch.sign(z_after - z_prev)
+    inner = soft_threshold_t(u - Ca, gamma1 * lambd)
+    midder = soft_threshold_t(inner - Cb + lambd * gamma1 * torch.sign(u - Ca), gamma2 * lambd)
+    return soft_threshold_t(midder + Cb - lambd * gamma1 * torch.sign(u - Ca), lambd)
+
+
+def forward_csr_t(y, A, B, t, s, D, sigma=None, adaptive=True, mask=1, z_prev=None, z_after=None, g_prev=None, g_after=None):
+    """The CSR forward loops restated on the torch-CPU operators of this oracle.  A, B, t: the operator set the
+    iterations use (CDLNet_CSR without z_prev: A2, B2, t2); D: the dictionary of the final synthesis (always B[0] of the
+    first set); g_prev / g_after: the (K,2,M,1,1) gamma parameters paired with z_prev / z_after (CDLNet_CSR: g;
+    CDLNet_CSRf2: g1 / g2).  Returns (xhat, z)."""
+    K = len(A)
+    yp, mean, pad, mp = pre_process_t(y, s, mask)
+    c = 0 if sigma is None or not adaptive else sigma / 255.0
+    thr = lambda p, k: p[k, :1] + c * p[k, 1:2]
+
+    def prox(u, k):
+        if z_prev is not None and z_after is not None:
+            return prox_csr_f2_t(u, z_prev, z_after, thr(t, k), thr(g_prev, k), thr(g_after, k))
+        if z_prev is not None:
+            return prox_csr_t(u, z_prev, thr(t, k), thr(g_prev, k))
+        if z_after is not None:
+            return prox_csr_t(u, z_after, thr(t, k), thr(g_after, k))
+        return soft_threshold_t(u, thr(t, k))
+    z = prox(analysis_t(yp, A[0], s), 0)
+    for k in range(1, K):
+        z = prox(z - analysis_t(mp * synthesis_t(z, B[k], s) - yp, A[k], s), k)
+    xp = synthesis_t(z, D, s)
+    return unpad_2d(xp, pad) + mean, z

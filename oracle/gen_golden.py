@@ -131,8 +131,71 @@ def nle_cases():
     print("wrote nle_mad.npz", {k: v.shape for k, v in out.items() if k.startswith("sigma_hat")})
 
 
+def csr_cases(ref):
+    """The frame-recurrent CSR networks of the unmodified reference (model/net.py:363-567), three consecutive frames each:
+    frame 0 without a neighbour, then with z_prev (CDLNet_CSR) / with every neighbour combination (CDLNet_CSRf2).
+        python oracle/gen_golden.py csr"""
+    def weights(net, gen, scale, names):
+        base = torch.randn(net.A[0].weight.shape, generator=gen) * scale
+        with torch.no_grad():
+            for k in range(net.K):
+                net.A[k].weight.data = base * (1 + 0.1 * torch.randn(base.shape, generator=gen))
+                net.B[k].weight.data = base * (1 + 0.1 * torch.randn(base.shape, generator=gen))
+                if hasattr(net, "A2"):
+                    net.A2[k].weight.data = base * (1 + 0.1 * torch.randn(base.shape, generator=gen))
+                    net.B2[k].weight.data = base * (1 + 0.1 * torch.randn(base.shape, generator=gen))
+            for nm in names:
+                p = getattr(net, nm)
+                v = torch.rand(p.shape, generator=gen) * (0.02 if nm.startswith("t") else 0.6)
+                v[:, 1] *= 2.0
+                p.data = v
+    out = {}
+    # CDLNet_CSR: argscsr.json's family reduced (P = 9, s = 2), ragged extents
+    g = torch.Generator().manual_seed(501)
+    net = ref.CDLNet_CSR(K=4, M=10, P=9, s=2, C=1, t0=0, adaptive=True, init=False).eval()
+    weights(net, g, 0.04, ("t", "t2", "g"))
+    frames = torch.rand(3, 2, 1, 27, 30, generator=g)           # (frame, N, C, H, W)
+    sig = torch.tensor([20.0, 35.0]).reshape(2, 1, 1, 1)
+    with torch.no_grad():
+        x0, z0 = net(frames[0], None, sig)
+        x1, z1 = net(frames[1], z0, sig)
+        x2, z2 = net(frames[2], z1, sig)
+    out.update(csr_frames=frames.numpy(), csr_sigma=sig.numpy(), csr_x=np.stack([x0.numpy(), x1.numpy(), x2.numpy()]),
+               csr_z=np.stack([z0.numpy(), z1.numpy(), z2.numpy()]), csr_s=np.int64(2))
+    for nm in ("t", "t2", "g"):
+        out["csr_" + nm] = getattr(net, nm).detach().numpy()
+    for nm in ("A", "B", "A2", "B2"):
+        out["csr_" + nm] = np.stack([m.weight.detach().numpy() for m in getattr(net, nm)])
+    # CDLNet_CSRf2: stride 1, colour, Bayer-like mask on; every neighbour combination
+    g = torch.Generator().manual_seed(502)
+    net = ref.CDLNet_CSRf2(K=3, M=8, P=7, s=1, C=3, t0=0, adaptive=True, init=False).eval()
+    weights(net, g, 0.03, ("t", "g1", "g2"))
+    y = torch.rand(1, 3, 20, 24, generator=g)
+    mask = ref._ref_root_utils.gen_bayer_mask(y)
+    y = mask * y
+    with torch.no_grad():
+        xa, za = net(y, None, None, 15.0, mask=mask)
+        zn1 = za * (1 + 0.3 * torch.randn(za.shape, generator=g)) + 0.01 * torch.randn(za.shape, generator=g) * (torch.rand(za.shape, generator=g) > 0.8)
+        zn2 = za * (1 + 0.3 * torch.randn(za.shape, generator=g))
+        xb, zb = net(y, zn1, None, 15.0, mask=mask)
+        xc, zc = net(y, None, zn2, 15.0, mask=mask)
+        xd, zd = net(y, zn1, zn2, 15.0, mask=mask)
+    out.update(f2_y=y.numpy(), f2_mask=mask.numpy(), f2_sigma=np.float64(15.0), f2_zprev=zn1.numpy(), f2_zafter=zn2.numpy(),
+               f2_x=np.stack([t_.numpy() for t_ in (xa, xb, xc, xd)]), f2_z=np.stack([t_.numpy() for t_ in (za, zb, zc, zd)]), f2_s=np.int64(1))
+    for nm in ("t", "g1", "g2"):
+        out["f2_" + nm] = getattr(net, nm).detach().numpy()
+    for nm in ("A", "B"):
+        out["f2_" + nm] = np.stack([m.weight.detach().numpy() for m in getattr(net, nm)])
+    np.savez_compressed(os.path.join(OUT, "csr.npz"), **out)
+    print("wrote csr.npz; nnz", float((z2 != 0).float().mean()), float((zd != 0).float().mean()),
+          "effect of the neighbours on xhat:", float((xb - xa).abs().max()), float((xd - xa).abs().max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["csr"]:
+        csr_cases(_refshim.load())
+        sys.exit(0)
     if sys.argv[1:] == ["nle"]:
         nle_cases()
         sys.exit(0)

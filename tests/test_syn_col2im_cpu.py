@@ -72,7 +72,7 @@ def lane_of(o):
     return 8 * (2 * (o >> 4) + (o & 1)) + ((o & 15) >> 1)
 
 
-def synthesize(z, w, od, Fd, nctas):
+def synthesize(z, w, od, Fd, nctas, sweep=False):
     N, M, Qd, Qh, Qw = z.shape
     Fh, Fw = 2 * Qh, 2 * Qw
     code = to_code(z)
@@ -88,18 +88,32 @@ def synthesize(z, w, od, Fd, nctas):
     src1, src2, srcm = [np.array([lane_of(v + d) for v in o]) for d in (1, 2, 31)]
     m1, m2, mm = (o < 31).astype(float), (o < 30).astype(float), (o > 0).astype(float)
     parts = [(0, 0, 13, 0), (13, 0, 12, 7 * 13), (25, 1, 12, 0), (37, 1, 12, 7 * 12)]   # (first row, half, rows, first column)
+    Fr = tiles_w * Qh                                               # tiles of one coarse frame
     for cta in range(nctas):
-        t0, t1 = T * cta // nctas, T * (cta + 1) // nctas
+        if sweep:                                                   # syn_tile, sweep = 1: a share of ONE frame, swept over all (n, qd)
+            a, ln = Fr * cta // nctas, Fr * (cta + 1) // nctas - Fr * cta // nctas
+            count = ln * N * Qd
+        else:
+            a, count = T * cta // nctas, T * (cta + 1) // nctas - T * cta // nctas
         X = np.zeros((XRING, XPL, XW))
         S = np.zeros((XRING, XPL, 4, 8))                          # seam columns: [0..2] left spill, [4..5] right spill per quadrant
-        for tau in range(t0, t1):
-            col, qh = divmod(tau, Qh)
-            qw0 = (col % tiles_w) * TILE_W
-            col //= tiles_w
-            qd, n = col % Qd, col // Qd
+        for i in range(count):
+            if sweep:
+                fi, j = divmod(i, ln)
+                wt, qh = divmod(a + j, Qh)
+                qw0 = wt * TILE_W
+                n, qd = divmod(fi, Qd)
+                first = j == 0 or qh == 0
+                last = j == ln - 1 or qh == Qh - 1
+            else:
+                tau = a + i
+                col, qh = divmod(tau, Qh)
+                qw0 = (col % tiles_w) * TILE_W
+                col //= tiles_w
+                qd, n = col % Qd, col // Qd
+                first = i == 0 or qh == 0
+                last = i == count - 1 or qh == Qh - 1
             row = (n * Qd + qd) * Qh + qh
-            first = tau == t0 or qh == 0
-            last = tau == t1 - 1 or qh == Qh - 1
             if first:
                 assert not X.any() and not S.any()                # the ring is clean when a run starts
             A = tma_tile(code, row, (qw0 >> 4) * 2, nrows, Qw)
@@ -154,6 +168,7 @@ def test_model_equals_conv_transpose3d(N, M, Qd, Qh, Qw, nctas):
     got = synthesize(z, w, od=3, Fd=2 * Qd, nctas=nctas)
     assert got.shape == ref.shape
     assert np.array_equal(got, ref)
+    assert np.array_equal(synthesize(z, w, od=3, Fd=2 * Qd, nctas=nctas, sweep=True), ref)       # frame-synchronous tile order
 
 
 def test_model_temporal_slab_offsets():
