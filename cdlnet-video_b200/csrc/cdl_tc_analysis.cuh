@@ -254,6 +254,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAThreads, 1) k_tc_a
     if (lane == 0) {
       const CUtensorMap* rmap = rank ? &rmap1 : &rmap0;     // odd sites read the copy shifted by two floats
       tma_prefetch_desc(rmap);
+      // (An L2 tensor prefetch of the residual boxes two tiles ahead was measured: the MMA warp's wait for r tiles fell from
+      //  15.5 % to 10.7 %, but the duplicated L2 traffic cost more - 0.641 vs 0.597 ms per launch on 16 clips, 22.6 vs 17.8 ms
+      //  on the 1080p clip, profiles/r02x_*.  Not kept.)
       int it = 0;
       for (int tile = pair; tile < p.ntiles; tile += npairs, ++it) {
         const int buf = it & 1;

@@ -443,8 +443,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
       for (int it = 0; it < rounds; ++it) {
         const SynTile t = syn_tile(p, share, it);
         const int g0 = (t.qw0 >> 4) * 2;                             // first group of the tile in its row
-        {                                                            // the next tile's 16 groups are one contiguous run: one L2 prefetch
-          const SynTile t2 = syn_tile(p, share, it + 1);
+        {                                                            // a tile's 16 groups are one contiguous run: one L2 prefetch
+          const SynTile t2 = syn_tile(p, share, it + 1);            // (distance 2 / no evict-first hint: same kernel time, profiles/r02x_*)
           if (t2.valid) {
             const int g2 = (t2.qw0 >> 4) * 2, ng = min(kSGroups, G - g2);
             bulk_prefetch_l2_hint(p.z + ((size_t)t2.row * G + g2) * kCodeGroup, (uint32_t)ng * kCodeGroup * 4, pol);

@@ -64,6 +64,9 @@ class _ISTANet(nn.Module):
     #: `auto` keeps the tensor-core kernels only if, on a calibration crop of the first input, they agree with the exact
     #: fp32 kernels to this max-abs deviation on xhat (the parity bar is 1e-4; the margin covers crop-vs-full variation)
     auto_tolerance = 6.5e-5
+    #: replay the forward from a CUDA graph (Plan.denoise_graphed): worth it for launch-bound inputs (one small image);
+    #: opt-in because the outputs are clones of static buffers and the first call per shape pays the capture
+    use_cuda_graph = os.environ.get("CDL_CUDA_GRAPH", "0") == "1"
 
     # -- plumbing ----------------------------------------------------------------------------------
     def __getstate__(self):
@@ -210,6 +213,8 @@ class _ISTANet(nn.Module):
             return self._forward_embedded3d(y, sigma)
         plan, y, mask, c = self._prepare(y, sigma, mask)
         with torch.cuda.device(y.device):
+            if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+                return plan.denoise_graphed(y, mask, c)
             return plan.denoise(y, mask, c)
 
     # -- 2-D stride-2 grayscale nets (CDLNet-s2030, BASELINE config 1) on the VIDEO tensor-core kernels ------------------

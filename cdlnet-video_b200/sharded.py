@@ -325,10 +325,46 @@ class ShardedVideoDenoiser:
         return xhat, (plan.export_code(self.code) if want_z else None)
 
     def denoise_host(self, y_host_slab, xhat_host_owned, sigma=None):
-        """Pinned host slab in, owned frames of xhat out into a pinned host buffer; asynchronous on the current stream."""
-        y = y_host_slab.to(self.plan.device, non_blocking=True)
-        xhat, _ = self.forward_resident(y, sigma)
-        xhat_host_owned.copy_(xhat, non_blocking=True)
+        """Pinned host slab in, owned frames of xhat out into a pinned host buffer.  Asynchronous: the upload runs on a
+        copy stream into one of two device buffers, the forward on the current stream, the download on a second copy stream,
+        so that in a sequence of calls (a stream of clips) the copies of neighbouring steps overlap the compute of this one
+        - every step still performs its own H2D and D2H.  The output buffer is complete after `den.wait()` (or a device
+        synchronisation)."""
+        dev = self.plan.device
+        cur = torch.cuda.current_stream(dev)
+        st = self.__dict__.setdefault("_io", None)
+        if st is None or st["shape"] != tuple(y_host_slab.shape):
+            st = self.__dict__["_io"] = {
+                "shape": tuple(y_host_slab.shape), "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev),
+                "ybuf": [torch.empty(y_host_slab.shape, dtype=torch.float32, device=dev) for _ in range(2)],
+                "free": [None, None], "flip": 0}
+        i = st["flip"]
+        st["flip"] ^= 1
+        with torch.cuda.stream(st["h2d"]):
+            if st["free"][i] is not None:
+                st["h2d"].wait_event(st["free"][i])          # the forward that last read this buffer (two calls ago) is done
+            st["ybuf"][i].copy_(y_host_slab, non_blocking=True)
+            up = st["h2d"].record_event()
+        cur.wait_event(up)
+        xhat, _ = self.forward_resident(st["ybuf"][i], sigma)
+        st["free"][i] = cur.record_event()
+        st["d2h"].wait_event(st["free"][i])
+        with torch.cuda.stream(st["d2h"]):
+            xhat_host_owned.copy_(xhat, non_blocking=True)
+        xhat.record_stream(st["d2h"])
+
+    def join(self):
+        """Make the current stream wait for the downloads of every enqueued denoise_host call (no host blocking)."""
+        st = self.__dict__.get("_io")
+        if st is not None:
+            torch.cuda.current_stream(self.plan.device).wait_stream(st["d2h"])
+
+    def wait(self):
+        """Block the host until every enqueued denoise_host call has delivered its output."""
+        st = self.__dict__.get("_io")
+        if st is not None:
+            st["d2h"].synchronize()
+        torch.cuda.current_stream(self.plan.device).synchronize()
 
     def __call__(self, y_slab, sigma=None):
         if y_slab.is_cuda:

@@ -94,3 +94,23 @@ def test_lockstep_slabs_cfg5_hyperparameters_vs_oracle():
     print(f"cfg5-like {D}x{H}x{W}, 4 slabs: sharded vs unsharded {e_su:.3e}; sharded vs oracle {e_so:.3e}; unsharded vs oracle {e_uo:.3e}; "
           f"nnz {float((zr != 0).float().mean()):.3f}")
     assert e_so <= 1e-4 and e_uo <= 1e-4 and e_su <= 1e-4, (e_su, e_so, e_uo)
+
+
+def test_denoise_host_pipelined_calls_deliver_each_clip():
+    """ShardedVideoDenoiser.denoise_host (the entry bench.py's e2e leg times): uploads / downloads run on copy streams and
+    overlap the forward of the neighbouring calls; three different clips enqueued back to back must each come back as their
+    own forward (exact fp32 family: bit-identical to forward_resident)."""
+    y, A, B, t = make_problem(seed=5, N=1, M=16, K=3, D=12, H=24, W=40)
+    net = _net(A, B, t, 2, (7, 7, 7))
+    d = torch.device("cuda", 0)
+    den = sharded.ShardedVideoDenoiser(net, tuple(y.shape), 0, 1, d, precision="fp32")
+    g = torch.Generator().manual_seed(1)
+    clips = [y] + [torch.rand(y.shape, generator=g) for _ in range(2)]
+    want = [den.forward_resident(c.to(d), 25.0)[0].cpu() for c in clips]
+    ins = [c.pin_memory() for c in clips]
+    outs = [torch.empty_like(c).pin_memory() for c in clips]
+    for a, b in zip(ins, outs):
+        den.denoise_host(a, b, 25.0)
+    den.wait()
+    for got, ref in zip(outs, want):
+        assert torch.equal(got, ref)
