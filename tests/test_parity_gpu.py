@@ -185,3 +185,30 @@ def test_errors_are_loud():
         plan.denoise(y, None, None)
     with pytest.raises(RuntimeError, match="not supported"):
         cb.Plan(2, 1, 1, 8, 2, (16, 16), (6, 6), 2)
+
+
+def test_gdlnet_filter_banks_are_synthesised_once_per_set_of_weights():
+    """GDLNet builds its 2K Gabor banks in torch (model/gabor.py:46-51, ~600 tiny launches): only when the parameters change,
+    not on every forward; a parameter update (version counter) or refresh_weights() rebuilds them."""
+    d = load_case("gdlnet_s2_c3")
+    net = module_from_case(d, "gdlnet_s2_c3").to(dev())
+    net.precision = "fp32"
+    y, sigma, mask = case_inputs(d, dev())
+    calls = {"n": 0}
+    orig = net._filter_banks
+
+    def counting():
+        calls["n"] += 1
+        return orig()
+    net._filter_banks = counting
+    with torch.no_grad():
+        x0, _ = net(y, sigma, mask=mask)
+        x1, _ = net(y, sigma, mask=mask)
+        assert calls["n"] == 1 and torch.equal(x0, x1)
+        net.A[0].alpha.mul_(1.01)                     # in-place update through autograd's version counter
+        x2, _ = net(y, sigma, mask=mask)
+        assert calls["n"] == 2 and not torch.equal(x2, x1)
+        net.A[0].alpha.data.mul_(1.0 / 1.01)          # a `.data` edit is invisible to the key ...
+        net.refresh_weights()                         # ... until the documented refresh
+        net(y, sigma, mask=mask)
+        assert calls["n"] == 3
