@@ -33,6 +33,7 @@
 // Warp roles (416 threads): warps 0-7 producers + flush (two per TMEM lane quadrant, half of the subbands each),
 // warps 8-11 col2im, warp 12 MMA issue + TMEM alloc.
 #pragma once
+#include <type_traits>
 #include "cdl_common.cuh"
 #include "cdl_tc_ptx.cuh"
 #include "cdl_tc2_analysis.cuh"
@@ -153,51 +154,85 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
     const uint32_t lane_addr = tbase + ((uint32_t)(quad * 32) << 16);
     const size_t plane = (size_t)p.H * p.W;
     float rg[32];
-    auto load_tile = [&](int tile) {
-      int n = 0, h0 = 0, w0 = 0, ok = 0;
-      if (tile < p.ntiles) {
-        syn_tile_coords(p, tile, n, h0, w0);
-        ok = (h0 + quad < p.H) && (w0 + lane < p.W);
-      }
-      const char* base = reinterpret_cast<const char*>(p.z + (((size_t)n * p.M + m0) * p.H + (h0 + quad)) * p.W + (w0 + lane));
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        rg[j] = ldg_f32_pred(base + (size_t)j * plane * 4, ok && j < nh && m0 + j < p.M);
+    // Tile coordinates are carried incrementally (tile += stride): the div / mod decode per use was 10 % of the kernel's
+    // instructions in an issue-bound kernel (ncu source page, profiles/r02ab_lines_tc2_synthesis.txt).
+    struct TileC { int n, th, tw; };
+    int sw, sh, sn;
+    { int t = stride; sw = t % p.tiles_w; t /= p.tiles_w; sh = t % p.tiles_h; sn = t / p.tiles_h; }
+    auto decode = [&](int tile) { TileC c; c.tw = tile % p.tiles_w; tile /= p.tiles_w; c.th = tile % p.tiles_h; c.n = tile / p.tiles_h; return c; };
+    auto advance = [&](TileC c) {
+      c.tw += sw; int cy = c.tw >= p.tiles_w; c.tw -= cy ? p.tiles_w : 0;
+      c.th += sh + cy; cy = c.th >= p.tiles_h; c.th -= cy ? p.tiles_h : 0;
+      c.n += sn + cy;
+      return c;
     };
-    // tile j of this CTA: out[c, h0-3+y, w0-3+x] += sum_r priv[r][c*7 + (y-r)][x]  over the rows r with 0 <= y-r <= 6
-    auto flush_tile = [&](int j) {
-      const int xb = j & 1;
-      int n, h0, w0;
-      syn_tile_coords(p, (int)blockIdx.x + j * stride, n, h0, w0);
-      mbar_wait(&xfull[xb], (j >> 1) & 1);
-      const float* pv = sP + xb * kPrivBuf;
-      const int nf = p.C * kFY * kFX;
-      for (int i = tid; i < nf; i += 32 * kSProdWarps) {
-        const int x = i % kFX, y = (i / kFX) % kFY, c = i / (kFX * kFY);
+    const int nvalid = max(0, min(nh, p.M - m0));                      // subbands this warp half really has
+    auto load_tile = [&](int tile, const TileC& c) {
+      const int h0 = c.th * kSTH, w0 = c.tw * kSTW;
+      const int ok = (tile < p.ntiles) && (h0 + quad < p.H) && (w0 + lane < p.W);
+      const int n = ok ? c.n : 0;
+      const char* base = reinterpret_cast<const char*>(p.z + (((size_t)n * p.M + m0) * p.H + (ok ? h0 + quad : 0)) * p.W + (ok ? w0 + lane : 0));
+      const size_t pitch = plane * 4;
+      if (nvalid == 32 && __all_sync(0xffffffffu, ok)) {                // interior tile, full subband half: unpredicated loads
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { rg[j] = ldg_f32_stream(base); base += pitch; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rg[j] = ldg_f32_pred(base + (size_t)j * pitch, ok && j < nvalid);
+      }
+    };
+    // flush of one tile: out[c, h0-3+y, w0-3+x] += sum_r priv[r][c*7 + (y-r)][x]  over the rows r with 0 <= y-r <= 6.
+    // Thread = one footprint column x of one channel c and one half of the 10 footprint rows: the (x, c, half) decode is done
+    // once per kernel, the row validity of the <= 4 terms is known at compile time, the output address advances by one image
+    // row.  (The element-per-thread form with a div / mod decode per output was 20 % of the kernel's instructions.)
+    const int fx = tid % kFPitch, fslot = tid / kFPitch;                // 40 columns (38 used) x 6 slots = 3 channels x 2 halves
+    const int fc = fslot >> 1, fhalf = fslot & 1;
+    const bool factive = fx < kFX && fc < p.C && fslot < 2 * kMaxC;
+    auto flush_rows = [&](auto HALF, const float* pv, int n, int h0, int w0) {
+      constexpr int Y0 = decltype(HALF)::value * (kFY / 2);
+      const int gw = w0 - kP / 2 + fx;
+      if (gw < 0 || gw >= p.W) return;
+      const float* pc = pv + fc * kP * kFPitch + fx;
+      size_t o = (((size_t)n * p.C + fc) * p.H) * p.W + gw;
+#pragma unroll
+      for (int yy = 0; yy < kFY / 2; ++yy) {
+        constexpr int dummy = 0; (void)dummy;
+        const int y = Y0 + yy;
         float v = 0.0f;
 #pragma unroll
         for (int r = 0; r < kSTH; ++r) {
           const int th = y - r;
-          if (th >= 0 && th < kP) v += pv[r * kPrivWarp + (c * kP + th) * kFPitch + x];
+          if (th >= 0 && th < kP) v += pc[r * kPrivWarp + th * kFPitch];
         }
-        const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;
-        if (gh >= 0 && gh < p.H && gw >= 0 && gw < p.W) {
-          const size_t o = (((size_t)n * p.C + c) * p.H + gh) * p.W + gw;
-          if (p.mask) v *= __ldg(p.mask + o);
-          red_add_f32(p.out + o, v);
+        const int gh = h0 - kP / 2 + y;
+        if (gh >= 0 && gh < p.H) {
+          const size_t oo = o + (size_t)gh * p.W;
+          if (p.mask) v *= __ldg(p.mask + oo);
+          red_add_f32(p.out + oo, v);
         }
+      }
+    };
+    auto flush_tile = [&](int j, const TileC& c) {
+      const int xb = j & 1;
+      mbar_wait(&xfull[xb], (j >> 1) & 1);
+      const float* pv = sP + xb * kPrivBuf;
+      if (factive) {
+        if (fhalf == 0) flush_rows(std::integral_constant<int, 0>{}, pv, c.n, c.th * kSTH, c.tw * kSTW);
+        else flush_rows(std::integral_constant<int, 1>{}, pv, c.n, c.th * kSTH, c.tw * kSTW);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&xfree[xb]);
     };
-    load_tile(blockIdx.x);
+    TileC ccur = decode(blockIdx.x), cprev = ccur, cnext;
+    load_tile(blockIdx.x, ccur);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += stride, ++it) {
       const int b = it & 1, u = it >> 1;
       uint32_t rt[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) rt[j] = tf32_rna_bits(rg[j]);
-      load_tile(tile + stride);
+      cnext = advance(ccur);
+      load_tile(tile + stride, cnext);
       mbar_wait(&aempty[b], (u & 1) ^ 1);
       tc_fence_after();
       const uint32_t acol = lane_addr + (uint32_t)(kSColA + b * kNMax + m0);
@@ -208,9 +243,10 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&afull[b]);
-      if (it > 0) flush_tile(it - 1);            // one tile behind: its col2im ran while this tile's A was produced
+      if (it > 0) flush_tile(it - 1, cprev);     // one tile behind: its col2im ran while this tile's A was produced
+      cprev = ccur; ccur = cnext;
     }
-    if (it > 0) flush_tile(it - 1);
+    if (it > 0) flush_tile(it - 1, cprev);
   } else if (warp < kSMmaWarp) {
     // ============================== col2im: accumulator -> write-once private footprint ==============================
     const int r = warp - kSProdWarps;

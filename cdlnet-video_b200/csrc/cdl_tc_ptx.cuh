@@ -267,6 +267,11 @@ __device__ __forceinline__ float ldg_f32_pred(const char* addr, int ok) {
                : "=f"(v) : "l"(addr), "r"(ok));
   return v;
 }
+__device__ __forceinline__ float ldg_f32_stream(const char* addr) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+  return v;
+}
 __device__ __forceinline__ void stg_f32_pred(char* addr, float v, int ok) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(ok) : "memory");
 }
