@@ -141,6 +141,7 @@ struct cdl_plan {
   bool tc2_ana_x3;     // CDL_PREC_TF32X3: 3-term (hi/lo) analysis (cdl_tc2_analysis_x3.cuh)
   bool tc2_maskpass;   // JDD mask applied by an image pass after the scatter-add instead of inside the footprint flush
   float* wB2;          // [K][Ng/8][176*8] tf32 filters in UMMA layout
+  float* wB2_lo;       // layer 0 only: tf32(W - tf32(W)), for the 3-term final synthesis
   size_t wB2_layer;
   int sm_count;
   bool have_weights;
@@ -465,6 +466,7 @@ extern "C" int cdl_plan_create(cdl_plan_t** out, const cdl_desc_t* d) {
     p->wB2_layer = (size_t)(p->tc2_Ng / 8) * tc2::kSN * 8;
     if ((e = cudaMalloc(&p->wA2, p->wA2_layer * g.K * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&p->wB2, p->wB2_layer * g.K * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&p->wB2_lo, p->wB2_layer * sizeof(float))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc2::syn_smem_bytes(tc2::kNMax))) != cudaSuccess ||
         (e = cudaFuncSetAttribute((const void*)tc2::k_tc2_analysis_x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -521,6 +523,7 @@ extern "C" void cdl_plan_destroy(cdl_plan_t* p) {
   if (p->wAtc) cudaFree(p->wAtc);
   if (p->wBtc) cudaFree(p->wBtc);
   if (p->wBtc_lo) cudaFree(p->wBtc_lo);
+  if (p->wB2_lo) cudaFree(p->wB2_lo);
   if (p->wA2) cudaFree(p->wA2);
   if (p->wB2) cudaFree(p->wB2);
   delete p;
@@ -639,8 +642,12 @@ extern "C" int cdl_set_weights(cdl_plan_t* p, const float* const* A, const float
       if (p->tc2_ana_x3) tc2::k_pack_tc2_analysis_x3<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
       else tc2::k_pack_tc2_analysis<<<32, 256, 0, st>>>(A[k], p->wA2 + (size_t)k * p->wA2_layer, g.M, g.C, p->tc2_Ng);
       CDL_LAUNCH_CHECK(p);
-      tc2::k_pack_tc2_synthesis<<<32, 256, 0, st>>>(B[k], p->wB2 + (size_t)k * p->wB2_layer, g.M, g.C, p->tc2_Ng);
+      tc2::k_pack_tc2_synthesis<<<32, 256, 0, st>>>(B[k], p->wB2 + (size_t)k * p->wB2_layer, g.M, g.C, p->tc2_Ng, 0);
       CDL_LAUNCH_CHECK(p);
+      if (k == 0) {
+        tc2::k_pack_tc2_synthesis<<<32, 256, 0, st>>>(B[0], p->wB2_lo, g.M, g.C, p->tc2_Ng, 1);
+        CDL_LAUNCH_CHECK(p);
+      }
     }
   }
   CDL_CUDA(cudaMemcpyAsync(p->t, t, (size_t)g.K * 2 * g.M * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -952,15 +959,17 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     }
     return CDL_OK;
   }
-  if (p->tc2_syn && residual) {
-    // residual synthesis of the 2-D stride-1 networks on the tensor cores; the final D z (residual == 0) stays on the
-    // exact fp32 kernel below: its rounding would land directly on xhat
+  if (p->tc2_syn && (residual || k == 0)) {
+    // 2-D stride-1 networks on the tensor cores.  Residual synthesis: one launch.  Final dictionary synthesis D z (residual == 0,
+    // D = B[0], model/net.py:90): its rounding lands directly on xhat, so it runs as the 3-term split
+    //   D z ~= hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W)      (three launches accumulating into out; 5.4 vs 15 ms on config 4
+    // for the exact fp32 kernel, which still serves residual == 0 with k != 0)
     cudaStream_t st = (cudaStream_t)stream_;
     const long long n4 = (long long)p->g.N * p->g.C * p->g.fine_vol() / 4;
     long long blocks = (n4 + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    const bool maskpass = p->desc.has_mask && p->tc2_maskpass;
-    if (maskpass) {
-      CDL_CUDA(cudaMemsetAsync(out, 0, (size_t)n4 * 16, st));            // out <- B z, then one image pass: mask * out - yp
+    const bool maskpass = residual && p->desc.has_mask && p->tc2_maskpass;
+    if (maskpass || !residual) {
+      CDL_CUDA(cudaMemsetAsync(out, 0, (size_t)n4 * 16, st));            // out <- B z (then, residual + mask: one image pass mask * out - yp)
     } else {
       tc::k_neg_copy<<<(int)blocks, 256, 0, st>>>(yp, out, n4);        // out <- -yp ; the scatter-add completes mask * B z - yp
       CDL_LAUNCH_CHECK(p);
@@ -969,7 +978,8 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     a.N = p->g.N; a.C = p->g.C; a.M = p->g.M; a.H = p->g.Fh; a.W = p->g.Fw;
     a.Kg = p->tc2_Ng;
     a.z = z; a.out = out;
-    a.mask = (p->desc.has_mask && !maskpass) ? mask_p : nullptr;
+    a.mask = (residual && p->desc.has_mask && !maskpass) ? mask_p : nullptr;
+    a.lo_code = 0;
     a.wpack = p->wB2 + (size_t)k * p->wB2_layer;
     a.tiles_w = ceil_div(p->g.Fw, tc2::kSTW);
     a.tiles_h = ceil_div(p->g.Fh, tc2::kSTH);
@@ -978,6 +988,14 @@ extern "C" int cdl_synthesis_step(cdl_plan_t* p, int k, int residual, const floa
     if (ctas > a.ntiles) ctas = a.ntiles;
     tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
     CDL_LAUNCH_CHECK(p);
+    if (!residual) {
+      a.lo_code = 1;
+      tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
+      CDL_LAUNCH_CHECK(p);
+      a.lo_code = 0; a.wpack = p->wB2_lo;
+      tc2::k_tc2_synthesis<<<ctas, tc2::kSThreads, tc2::syn_smem_bytes(a.Kg), st>>>(a);
+      CDL_LAUNCH_CHECK(p);
+    }
     if (maskpass) {
       tc2::k_mask_residual<<<(int)blocks, 256, 0, st>>>(out, mask_p, yp, n4);
       CDL_LAUNCH_CHECK(p);

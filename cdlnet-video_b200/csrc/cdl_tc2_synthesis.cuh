@@ -57,6 +57,7 @@ struct Syn2Params {
   const float* z;       // (N, M, H, W)
   float* out;           // (N, C, H, W), accumulated into
   const float* mask;    // (N, C, H, W) or nullptr: multiplies B z
+  int lo_code;          // 1: A = tf32(z - tf32(z)), the low part of the code (second term of the 3-term final D z)
   const float* wpack;   // this layer: [Kg/8 k-steps][22 groups][2][8][4] tf32-rounded filters
   int tiles_w, tiles_h, ntiles;
 };
@@ -64,14 +65,16 @@ struct Syn2Params {
 __host__ __device__ inline uint32_t syn_b_bytes(int Kg) { return (uint32_t)(Kg / 8) * kSN * 32u; }
 
 // filters (M,C,7,7) [ConvTranspose2d weight (in = M, out = C, th, tw)] -> B[n = (c*7 + th)*8 + tw, k = m], UMMA K-major
-__global__ void k_pack_tc2_synthesis(const float* __restrict__ w, float* __restrict__ out, int M, int C, int Kg) {
+// lo != 0: the part of W that tf32 rounding drops, tf32(W - tf32(W)) (3-term final dictionary synthesis)
+__global__ void k_pack_tc2_synthesis(const float* __restrict__ w, float* __restrict__ out, int M, int C, int Kg, int lo = 0) {
   const int total = (Kg / 8) * kSN * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i % 4, r8 = (i / 4) % 8, kc = (i / 32) % 2, grp = (i / 64) % (kSN / 8), ks = i / (kSN * 8);
     const int n = grp * 8 + r8, m = ks * 8 + kc * 4 + e;
     const int row = n >> 3, tw = n & 7, c = row / kP, th = row % kP;
     const float v = (row < kP * C && tw < kP && m < M) ? w[(((size_t)m * C + c) * kP + th) * kP + tw] : 0.0f;
-    out[i] = ptx::to_tf32_rna(v);
+    const float hi = ptx::to_tf32_rna(v);
+    out[i] = lo ? ptx::to_tf32_rna(v - hi) : hi;
   }
 }
 
@@ -231,6 +234,10 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
       uint32_t rt[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) rt[j] = tf32_rna_bits(rg[j]);
+      if (p.lo_code) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rt[j] = tf32_rna_bits(__fsub_rn(rg[j], __uint_as_float(rt[j])));
+      }
       cnext = advance(ccur);
       load_tile(tile + stride, cnext);
       mbar_wait(&aempty[b], (u & 1) ^ 1);

@@ -195,3 +195,34 @@ def test_cuda_graph_replay_matches_eager_and_is_faster_on_a_small_image():
         net.use_cuda_graph = False
         x3, _ = net(y, 25.0)
     assert torch.equal(x2, x3) and not torch.equal(x2, x1)
+
+
+@pytest.mark.parametrize("N,C,M,H,W", [(2, 3, 64, 40, 72), (1, 1, 32, 33, 64), (1, 3, 20, 21, 44)])
+def test_final_dictionary_synthesis_three_term_split_vs_fp32_kernel(N, C, M, H, W):
+    """D z (residual = 0, k = 0) on the tensor cores as hi(z) hi(W) + lo(z) hi(W) + hi(z) lo(W): bit-exact on integer data
+    (the low parts vanish), fp32-class on real data (the dropped lo*lo term is 2^-22 relative per product)."""
+    torch.manual_seed(7 * N + M)
+    dev = torch.device("cuda", 0)
+    ref, tc = _plans(N, C, M, 2, H, W)
+    t = torch.zeros(2, 2, M, device=dev)
+    for integer in (True, False):
+        if integer:
+            Bw = [torch.randint(-4, 5, (M, C, 7, 7), device=dev).float() / 8 for _ in range(2)]
+            z = torch.randint(-8, 9, (N, M, H, W), device=dev).float()
+        else:
+            Bw = [torch.randn(M, C, 7, 7, device=dev) * 0.05 for _ in range(2)]
+            z = torch.randn(N, M, H, W, device=dev)
+        z = z * (torch.rand_like(z) < 0.3)
+        for pl in (ref, tc):
+            pl.set_weights(Bw, Bw, t)
+        oa = torch.empty(N, C, H, W, device=dev)
+        ob = torch.empty_like(oa)
+        n0 = tc.launch_count()
+        ref.synthesis_step(0, z, oa, residual=False)
+        tc.synthesis_step(0, z, ob, residual=False)
+        torch.cuda.synchronize()
+        assert tc.launch_count() - n0 == 3                               # three tensor-core launches (+ a memset), no fp32 kernel
+        if integer:
+            assert torch.equal(oa, ob)
+        else:
+            assert (oa - ob).abs().max().item() <= 4e-6 * max(1.0, oa.abs().max().item())
