@@ -146,7 +146,7 @@ SSRC = open(SHDR).read()
 def test_synthesis_constants():
     assert "constexpr int kSTH = 4, kSTW = 32;" in SSRC and "constexpr int kSN = 176;" in SSRC
     assert "__shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);" in SSRC
-    assert "const int gh = h0 - kP / 2 + y, gw = w0 - kP / 2 + x;" in SSRC
+    assert "const int gw = w0 - kP / 2 + fx;" in SSRC and "const int gh = h0 - kP / 2 + y;" in SSRC
     # TMEM budget: two accumulators + two A slots
     assert 2 * 176 + 2 * 64 <= 512
 
@@ -172,7 +172,9 @@ V2SRC = SSRC
 
 
 def test_synthesis_source_matches_model():
-    assert "if (th >= 0 && th < kP) v += pv[r * kPrivWarp + (c * kP + th) * kFPitch + x];" in V2SRC
+    # flush: a thread walks footprint column fx of channel fc; pc = pv + fc * kP * kFPitch + fx
+    assert "const float* pc = pv + fc * kP * kFPitch + fx;" in V2SRC
+    assert "if (th >= 0 && th < kP) v += pc[r * kPrivWarp + th * kFPitch];" in V2SRC
     assert "row[lane] = own;" in V2SRC and "if (lane < kP - 1) row[32 + lane] = spill;" in V2SRC
     assert "put_row(&cur[8 * q], priv + (4 * g + q) * kFPitch);" in V2SRC
     assert "tmem_ld32(dcol + 32 * (g + 1), nxt);" in V2SRC and "tmem_ld8(dcol + 160," in V2SRC
