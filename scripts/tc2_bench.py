@@ -50,8 +50,7 @@ def main():
         outs = {}
         # arms: fp32 = exact CUDA-core kernels (CDL_TC2D=0), tc2 = tensor-core analysis + residual synthesis (the default),
         # tc2fm = the same with the JDD mask applied inside the footprint flush (CDL_TC2D_MASKPASS=0),
-        # tc2v2 = the candidate col2im of cdl_tc2_synthesis_v2.cuh (CDL_TC2D_SYN=2),
-        # tc2x3 = the candidate 3-term analysis of cdl_tc2_analysis_x3.cuh (CDL_TC2D_ANA=3)
+        # tc2x3 = the 3-term (hi/lo) analysis of cdl_tc2_analysis_x3.cuh (precision "tf32x3")
         arms = os.environ.get("TC2_ARMS", "fp32,tc2").split(",")
         for tag in arms:
             net.__dict__.pop("_plans", None)

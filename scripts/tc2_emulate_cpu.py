@@ -21,7 +21,7 @@ def tf32(x):
 
 
 def forward(d, analysis="tf32"):
-    """analysis: "tf32" = the default kernels; "3term" = the hi/lo analysis of cdl_tc2_analysis_x3.cuh (CDL_TC2D_ANA=3)."""
+    """analysis: "tf32" = the default kernels; "3term" = the hi/lo analysis of cdl_tc2_analysis_x3.cuh (precision "tf32x3")."""
     y = torch.from_numpy(d["y"])
     A = [torch.from_numpy(a) for a in d["A"]]
     B = [torch.from_numpy(b) for b in d["B"]]

@@ -1,4 +1,4 @@
-"""The algebra behind the opt-in CDL_EMBED3D route (cdlnet-video_b200/model/net.py::_forward_embedded3d): a 2-D stride-2
+"""The algebra behind the two-frame embedding route (default for config 1; CDL_EMBED3D=0 disables) (cdlnet-video_b200/model/net.py::_forward_embedded3d): a 2-D stride-2
 7x7 network is the video network on a two-frame clip (image, zero) with each filter in the td = 3 slice of a 7x7x7
 filter.  Checked here with torch's own convolutions (the reference's arithmetic): analysis, synthesis, and a whole
 ISTA iteration agree with the 2-D operators, frame 1 stays zero."""

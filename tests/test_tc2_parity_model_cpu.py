@@ -36,7 +36,7 @@ def test_predicted_parity_on_reference_golden_vectors(name, bound):
 
 @pytest.mark.parametrize("name", ["cdlnet2d_jdd_s1_w4", "gdlnet_s1_c3", "cdlnet2d_nonadaptive"])
 def test_three_term_analysis_model(name):
-    """The candidate accurate mode (cdl_tc2_analysis_x3.cuh, CDL_TC2D_ANA=3): u = r_hi W_hi + r_lo W_hi + r_hi W_lo.
+    """The accurate mode (cdl_tc2_analysis_x3.cuh, precision "tf32x3"): u = r_hi W_hi + r_lo W_hi + r_hi W_lo.
     With it the remaining error is the residual synthesis's; it must not be worse than the single-pass analysis."""
     d = load_case(name)
     e1 = np.abs(forward(d)[0].numpy() - d["xhat"]).max()
