@@ -44,9 +44,9 @@ enum cdl_status {
 enum cdl_precision {
   CDL_PREC_FP32 = 0, /* CUDA-core fp32 FMA: same arithmetic class as the reference on CPU  */
   CDL_PREC_TF32X3 = 2, /* like TF32 with the ANALYSIS convolution as a 3-term split, r_hi W_hi + r_lo W_hi + r_hi W_lo (fp32-class
-                      * accuracy of the step that carries the error at large K, ~2.2x its tensor time).  2-D stride-1
+                      * accuracy of the step that carries the error at large K, ~1.6x the analysis time).  2-D stride-1
                       * geometries only; elsewhere the FP32 kernels run.                                              */
-  CDL_PREC_TF32 = 1  /* tcgen05 kind::tf32, operands rounded RNE, fp32 accumulate in TMEM.
+  CDL_PREC_TF32 = 1  /* tcgen05 kind::tf32, operands rounded RNE, fp32 accumulate in TMEM; the final D z as a 3-term (hi/lo) split.
                       * Covered geometries: the video network (3-D, 7x7x7, s = 2, C = 1, M <= 176, model/net.py:123-143)
                       * and the 2-D stride-1 networks (7x7, s = 1, C <= 3, M <= 64, padded width % 4 == 0:
                       * model/net.py:20-36 with args.json / JDD args, GDLNet :572-600); any other geometry gets the
