@@ -196,10 +196,12 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
       const int gw = w0 - kP / 2 + fx;
       if (gw < 0 || gw >= p.W) return;
       const float* pc = pv + fc * kP * kFPitch + fx;
-      size_t o = (((size_t)n * p.C + fc) * p.H) * p.W + gw;
+      const int gh0 = h0 - kP / 2 + Y0;                                 // image row of this thread's first footprint row
+      const long long o = (((long long)n * p.C + fc) * p.H + gh0) * p.W + gw;      // may point above the image: only dereferenced in range
+      float* po = p.out + o;
+      const float* pm = p.mask ? p.mask + o : nullptr;
 #pragma unroll
       for (int yy = 0; yy < kFY / 2; ++yy) {
-        constexpr int dummy = 0; (void)dummy;
         const int y = Y0 + yy;
         float v = 0.0f;
 #pragma unroll
@@ -207,12 +209,13 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
           const int th = y - r;
           if (th >= 0 && th < kP) v += pc[r * kPrivWarp + th * kFPitch];
         }
-        const int gh = h0 - kP / 2 + y;
+        const int gh = gh0 + yy;
         if (gh >= 0 && gh < p.H) {
-          const size_t oo = o + (size_t)gh * p.W;
-          if (p.mask) v *= __ldg(p.mask + oo);
-          red_add_f32(p.out + oo, v);
+          if (pm) v *= __ldg(pm);
+          red_add_f32(po, v);
         }
+        po += p.W;
+        if (pm) pm += p.W;
       }
     };
     auto flush_tile = [&](int j, const TileC& c) {
@@ -260,12 +263,16 @@ __global__ void __launch_bounds__(kSThreads, 1) k_tc2_synthesis(const Syn2Params
     const uint32_t lane_addr = tbase + ((uint32_t)(r * 32) << 16);
     // one (c,th) row: combine the 7 w-taps across lanes (lane L receives tap tw of lane (L - tw) mod 32: its own column for
     // L >= tw, the spill column 32 + L otherwise) and WRITE columns L and 32 + L of the private row
+    // (the lane >= tw test as two 0/1 weights: two FFMAs per tap and no select - exact, the weights are 0 and 1)
+    float mo[kP], ms[kP];
+#pragma unroll
+    for (int tw = 1; tw < kP; ++tw) { mo[tw] = lane >= tw ? 1.0f : 0.0f; ms[tw] = 1.0f - mo[tw]; }
     auto put_row = [&](const uint32_t* v, float* row) {
       float own = __uint_as_float(v[0]), spill = 0.0f;
 #pragma unroll
       for (int tw = 1; tw < kP; ++tw) {
         const float w = __shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);
-        if (lane >= tw) own += w; else spill += w;
+        own = fmaf(w, mo[tw], own); spill = fmaf(w, ms[tw], spill);
       }
       row[lane] = own;
       if (lane < kP - 1) row[32 + lane] = spill;

@@ -146,7 +146,7 @@ SSRC = open(SHDR).read()
 def test_synthesis_constants():
     assert "constexpr int kSTH = 4, kSTW = 32;" in SSRC and "constexpr int kSN = 176;" in SSRC
     assert "__shfl_sync(0xffffffffu, __uint_as_float(v[tw]), (lane - tw) & 31);" in SSRC
-    assert "const int gw = w0 - kP / 2 + fx;" in SSRC and "const int gh = h0 - kP / 2 + y;" in SSRC
+    assert "const int gw = w0 - kP / 2 + fx;" in SSRC and "const int gh0 = h0 - kP / 2 + Y0;" in SSRC
     # TMEM budget: two accumulators + two A slots
     assert 2 * 176 + 2 * 64 <= 512
 
