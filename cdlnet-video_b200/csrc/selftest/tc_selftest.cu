@@ -2,7 +2,7 @@
 // Each case computes D[128*CG x N] = A[128*CG x K] * B[N x K]^T (tf32, fp32 accumulate) with operands
 // that are exactly representable, so any mismatch is a layout / descriptor error, not rounding.
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o tc_selftest tc_selftest.cu
-//   run  : ./tc_selftest <cg:1|2> <ts:0|1> <N> <KS>
+//   run  : ./tc_selftest <cg:1|2> <ts:0|1> <N> <KS> [rep probe commit_every overlap nclusters]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
 int main(int argc, char** argv) {
   int cg = argc > 1 ? atoi(argv[1]) : 1, ts = argc > 2 ? atoi(argv[2]) : 0, N = argc > 3 ? atoi(argv[3]) : 176, KS = argc > 4 ? atoi(argv[4]) : 7;
   int rep = argc > 5 ? atoi(argv[5]) : 1, probe = argc > 6 ? atoi(argv[6]) : 0, cgroup = argc > 7 ? atoi(argv[7]) : 0, ovl = argc > 8 ? atoi(argv[8]) : 0;
+  const int nclusters = argc > 9 ? atoi(argv[9]) : 1;   // > 1: the same GEMM on that many clusters at once (whole-chip MMA rate; every cluster writes the same D)
   const int M = 128 * cg, K = KS * 8;
   std::vector<float> A((size_t)M * K + (size_t)2 * 128 * K + 2 * KS * 1024), B((size_t)N * K), Bp((size_t)N * K), D((size_t)M * N, -1.f), R((size_t)M * N);
   uint32_t s = 12345;
@@ -186,7 +187,7 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dD, D.data(), D.size() * 4, cudaMemcpyHostToDevice));
   size_t smem = ((size_t)KS * (N / cg) * 8 + (size_t)KS * 1024) * 4 + 1024;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cg); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(cg * nclusters); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
