@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
 #ifdef SELFTEST_WARP_ISSUE
   if (rank == 0 && warp == 0) {      // converged warp, elected lane issues
 #ifdef SELFTEST_CONST
+#ifndef SELFTEST_KS
+#define SELFTEST_KS 7        // K-steps (distinct operand pairs) the constant-operand loop cycles through; run with the same KS argument
+#endif
     if (tbase != 0) __trap();
     const uint32_t idesc = make_idesc_tf32(128 * CG, 176);
     const uint64_t bd0 = make_smem_desc_kmajor_noswz(smem_u32(smem), 128, 256);
@@ -75,12 +78,12 @@ __global__ void __launch_bounds__(128) k_gemm(const float* __restrict__ A, const
     for (int r = 0; r < rep; ++r) {
       if (TS) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j)
+        for (int j = 0; j < SELFTEST_KS; ++j)
           mma_tf32_ts_warp<CG>(0, ACOL + j * 8, bd0 + (uint64_t)((j * (176 / CG) * 32) >> 4), idesc, 1);
       } else {
-        const uint64_t ad0 = make_smem_desc_kmajor_noswz(smem_u32(smem) + 7 * (176 / CG) * 32, 16, 144);
+        const uint64_t ad0 = make_smem_desc_kmajor_noswz(smem_u32(smem) + SELFTEST_KS * (176 / CG) * 32, 16, 144);
 #pragma unroll
-        for (int j = 0; j < 7; ++j)
+        for (int j = 0; j < SELFTEST_KS; ++j)
           mma_tf32_ss_warp<CG>(0, ad0 + (uint64_t)((j * 4096) >> 4), bd0 + (uint64_t)((j * (176 / CG) * 32) >> 4), idesc, 1);
       }
       if (cgroup > 0) mma_commit_warp<CG>(&bar2[r & 7]);
