@@ -36,3 +36,15 @@ def test_windows_equal_independent_calls(D, use_mask, per_sample):
             with torch.no_grad():
                 ref, _ = net(clip[n:n + 1, :, a:b], s, mask=m)
             assert torch.allclose(out[n:n + 1, :, a:b], ref, atol=1e-6), (a, b, n)
+
+
+def test_noisy_forward_has_no_cpu_route():
+    """windows.noisy_forward is the fused input pipeline of the CUDA path (cdl_preprocess_noisy): a CPU tensor must fail
+    loudly, not fall back (the modules' own forward keeps the stock torch route for CPU tensors)."""
+    import pytest
+    import torch
+    import cdlnet_video_b200 as cb
+    from cdlnet_video_b200 import windows
+    net = cb.CDLNetVideo(K=2, M=4, P=7, s=2, C=1, adaptive=True, init=False).eval()
+    with pytest.raises(RuntimeError, match="CUDA fp32"):
+        windows.noisy_forward(net, torch.rand(1, 1, 4, 8, 8), 25.0, torch.randn(1, 1, 4, 8, 8))
