@@ -41,14 +41,21 @@ constexpr int kNBP = 176;                 // GEMM N per tap half
 constexpr int kRowsP0 = 25;               // (th,td) rows of 7 taps in half 0 (half 1: 24)
 constexpr int kSTileW = 128;              // coarse sites per tile: one row, 8 blocks of 16 = 16 groups of 8
 constexpr int kSGroups = kSTileW / 8;
-constexpr int kSChunkKS = 4;              // K-steps per A ring slot (the last chunk of a tile holds 2: the TMA box runs past the
+#ifndef CDL_SYN_KS
+#define CDL_SYN_KS 4
+#endif
+#ifndef CDL_SYN_SLOTS
+#define CDL_SYN_SLOTS 3
+#endif
+constexpr int kSChunkKS = CDL_SYN_KS;      // K-steps per A ring slot (the last chunk of a tile holds 2: the TMA box runs past the
                                           // 176 subbands and is zero-filled there)
 constexpr int kSChunkK4 = 2 * kSChunkKS;  // 4-subband chunks per slot
 constexpr int kSChunkFloats = kSGroups * kSChunkK4 * kCodeChunk;     // 4096 floats = 16 KB
 constexpr int kSChunks = (kKBSteps + kSChunkKS - 1) / kSChunkKS;     // 6 chunks per tile
-constexpr int kSSlots = 3;                // A ring depth: 48 KB in flight.  Every slot is used exactly twice per tile, so slot AND
+constexpr int kSSlots = CDL_SYN_SLOTS;    // A ring depth: 48 KB in flight.  Every slot is used exactly twice per tile, so slot AND
                                           // barrier parity of chunk c are compile-time (c % 3, c / 3).  Measured: a wait + commit pair
                                           // costs the issuing warp ~300 cycles, so it must be amortised over >= 8 MMAs (704 pipe cycles)
+static_assert(kSChunks % kSSlots == 0 && (kSChunks / kSSlots) % 2 == 0, "every slot must be used an even number of times per tile (compile-time barrier parities)");
 constexpr int kXW = 264;                  // footprint columns: col c <-> fine w = 2*qw0 - 4 + c (cols 1..261 used)
 constexpr int kXPl = 7;                   // fine frames of one coarse frame's footprint
 constexpr int kXRing = 7;                 // ring of fine rows: the 2 rows a tile finishes are flushed (by the same warps) before the
@@ -327,11 +334,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSynThreads, 1) k_tc
             return __uint_as_float(__float_as_uint(z - hi) + kCodeBias);
           };
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {                                                 // 512 threads x 2 x 16 B = one chunk
-            float4* pa = reinterpret_cast<float4*>(sA + slot * kSChunkFloats) + h * 32 * kSynC2iWarps + tid;
-            float4 w = *pa;
-            w.x = lo_word(w.x); w.y = lo_word(w.y); w.z = lo_word(w.z); w.w = lo_word(w.w);
-            *pa = w;
+          for (int h = 0; h * 32 * kSynC2iWarps < kSChunkFloats / 4; ++h) {             // 512 threads x 16 B per step
+            const int idx = h * 32 * kSynC2iWarps + tid;
+            if (idx < kSChunkFloats / 4) {
+              float4* pa = reinterpret_cast<float4*>(sA + slot * kSChunkFloats) + idx;
+              float4 w = *pa;
+              w.x = lo_word(w.x); w.y = lo_word(w.y); w.z = lo_word(w.z); w.w = lo_word(w.w);
+              *pa = w;
+            }
           }
           fence_async_smem();
           __syncwarp();
