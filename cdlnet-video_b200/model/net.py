@@ -109,10 +109,35 @@ class _ISTANet(nn.Module):
         if plan is None:
             if len(plans) >= 8:
                 plans.pop(next(iter(plans))).close()
-            plan = Plan(self._nsp, shape[0], shape[1], self.M, self.K, tuple(shape[2:]), self._P3(), self.s,
+            plan = Plan(self._nsp, shape[0], shape[1], self.M, self.K, tuple(shape[2:]), self._plan_P(prec), self.s,
                         has_mask=has_mask, precision=prec, device=device_index or 0)
             plans[key] = plan
         return plan
+
+    def _plan_P(self, prec):
+        """Filter extents the plan is created with.  The video tensor-core kernels are written for 7x7x7 (stride 2, C = 1,
+        M <= 176); any smaller odd extents (the constructor's default (7,7,5), (5,5,5), ...) are the same operator with the
+        filters zero-embedded in the centre of a 7x7x7 box - padding P//2 and the output extents are unchanged - so the
+        tensor-core families get the embedded geometry (2/7 of the MMAs multiply zeros for (7,7,5)); the exact fp32 family
+        keeps the native extents."""
+        P = self._P3()
+        if (prec != "fp32" and self._nsp == 3 and self.s == 2 and self._in_channels() == 1 and self.M <= 176
+                and P != (7, 7, 7) and all(q % 2 == 1 and q <= 7 for q in P)):
+            return (7, 7, 7)
+        return P
+
+    def _banks_for(self, plan, A=None, B=None):
+        """filter banks in the extents `plan` was created with (zero-embedded when the plan is wider than the filters)"""
+        if A is None:
+            A, B = self._filter_banks()
+        want = tuple(plan.Pfull[-self._nsp:])
+        have = tuple(A[0].shape[2:])
+        if want == have:
+            return A, B
+        pad = []
+        for w_, h_ in zip(reversed(want), reversed(have)):         # F.pad order: innermost axis first
+            pad += [(w_ - h_) // 2, (w_ - h_) // 2]
+        return [F.pad(a.detach(), pad) for a in A], [F.pad(b.detach(), pad) for b in B]
 
     def _weights_key(self):
         """Identity of the current weights: (storage, version counter) of every parameter plus an epoch that
@@ -134,7 +159,7 @@ class _ISTANet(nn.Module):
             key = None                   # parameters are expected to move: never trust a cached pack
         if key is not None and plan._weights_key == key:
             return                       # (GDLNet: the Gabor banks are not even synthesised)
-        A, B = self._filter_banks()
+        A, B = self._banks_for(plan)
         plan.set_weights(A, B, self.t, key=key)
 
     def _precision_for(self, y, mask, c, key):
@@ -170,9 +195,9 @@ class _ISTANet(nn.Module):
                     return ("tf32", None)        # no tensor-core kernel for this geometry: the request resolves to the fp32 family anyway
                 continue                          # no 3-term kernel for this geometry (video): next stop is fp32
             if ref is None:
-                p_ex.set_weights(A, B, self.t)
+                p_ex.set_weights(*self._banks_for(p_ex, A, B), self.t)
                 ref = p_ex.denoise(yc, mc, cc, want_z=False)[0]
-            p_tc.set_weights(A, B, self.t)
+            p_tc.set_weights(*self._banks_for(p_tc, A, B), self.t)
             dev = float((p_tc.denoise(yc, mc, cc, want_z=False)[0] - ref).abs().max())
             if dev <= self.auto_tolerance:
                 return (family, dev)

@@ -156,3 +156,29 @@ def test_stepwise_rearm_opt_in():
     assert launches[1] == launches[0] - (K - 2)        # synthesis k = 2..K-1 skipped its -yp pass
     assert (outs[0][0] - outs[1][0]).abs().max().item() <= 1e-4      # run-to-run scatter-add order, as above
     assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("P", [(7, 7, 5), (5, 5, 5), (7, 5, 3)])
+def test_smaller_filters_run_on_the_tensor_core_kernels_zero_embedded(P):
+    """CDLNetVideo with odd filter extents below 7 (the constructor's default (7,7,5), model/net.py:126): the tensor-core family
+    gets the filters zero-embedded in a 7x7x7 box (model/net.py::_plan_P) - same operator, same output extents."""
+    import cdl_oracle as O
+    torch.manual_seed(sum(P))
+    K, M = 3, 24
+    net = cb.CDLNetVideo(K=K, M=M, P=P, s=2, C=1, t0=0.0, adaptive=True, init=False)
+    with torch.no_grad():
+        for k in range(K):
+            net.A[k].weight.mul_(0.7 / np.sqrt(2.0 * M * np.prod(P) / 8))
+            net.B[k].weight.copy_(net.A[k].weight * (1 + 0.05 * torch.randn_like(net.A[k].weight)))
+        net.t.copy_(torch.rand_like(net.t) * 0.01)
+    y = torch.rand(1, 1, 10, 28, 36)
+    xr, zr, *_ = O.forward_t(y, [m.weight.detach() for m in net.A], [m.weight.detach() for m in net.B], net.t.detach(), 2, 25.0, True, 1)
+    net = net.cuda().eval()
+    for prec in ("tf32", "fp32"):
+        net.precision = prec
+        with torch.no_grad():
+            xhat, z = net(y.cuda(), 25.0)
+        assert net._last_plan.precision == prec
+        assert tuple(net._last_plan.Pfull) == ((7, 7, 7) if prec == "tf32" else P)
+        assert tuple(xhat.shape) == tuple(xr.shape) and tuple(z.shape) == tuple(zr.shape)
+        assert (xhat.cpu() - xr).abs().max().item() <= (1e-4 if prec == "tf32" else 2e-5)
