@@ -283,14 +283,20 @@ class ShardedVideoDenoiser:
     def __init__(self, net, clip_shape, rank, world, device, precision="tf32", group=None):
         from .plan import Plan
         N, C, D, H, W = clip_shape
-        P3 = net._P3()
-        self.geo = slab_geometry(D, P3[0], net.s, world, rank)
+        P3 = net._plan_P(precision)                  # (7,7,7) when smaller odd filters ride the tensor-core kernels zero-embedded:
+        self.geo = slab_geometry(D, P3[0], net.s, world, rank)      # the halos then follow the embedded temporal extent
         g = self.geo
         dev_index = torch.device(device).index or 0
         plan = Plan(3, N, C, net.M, net.K, (g["f1"] - g["f0"], H, W), P3, net.s, precision=precision, device=dev_index,
                     halo_front=g["hf"], halo_back=g["hb"])
         sum_plan = Plan(3, N, C, net.M, 1, (net.s * (g["q1"] - g["q0"]), H, W), P3, net.s, precision="fp32", device=dev_index)
-        A, B = net._filter_banks()
+        if plan.precision == "fp32" and P3 != net._P3():     # the tensor-core kernels declined (odd width, ...): native extents
+            plan.close()
+            P3 = net._P3()
+            self.geo = g = slab_geometry(D, P3[0], net.s, world, rank)
+            plan = Plan(3, N, C, net.M, net.K, (g["f1"] - g["f0"], H, W), P3, net.s, precision="fp32", device=dev_index,
+                        halo_front=g["hf"], halo_back=g["hb"])
+        A, B = net._banks_for(plan)
         plan.set_weights(A, B, net.t)
         self.net, self.plan, self.sum_plan = net, plan, sum_plan
         self.state = SlabRank(PlanOps(plan, sum_plan), g, net.K, net.s)

@@ -114,3 +114,29 @@ def test_denoise_host_pipelined_calls_deliver_each_clip():
     den.wait()
     for got, ref in zip(outs, want):
         assert torch.equal(got, ref)
+
+
+def test_lockstep_slabs_with_zero_embedded_filters():
+    """A video net with filters (5,7,7) on the tensor-core kernels (zero-embedded in 7x7x7, model/net.py::_plan_P): the slab
+    geometry follows the embedded temporal extent; 2 slabs in lock step equal the unsharded forward and the oracle."""
+    import torch.nn.functional as F
+    import cdl_oracle as O
+    y, A7, B7, t = make_problem(seed=9, N=1, M=24, K=3, D=24, H=24, W=40)
+    A = [a[:, :, 1:6].contiguous() for a in A7]                  # crop the temporal extent 7 -> 5
+    B = [b[:, :, 1:6].contiguous() for b in B7]
+    net = _net(A, B, t, 2, (5, 7, 7))
+    net.precision = "tf32"
+    d = torch.device("cuda", 0)
+    with torch.no_grad():
+        xr, _ = net(y.to(d), 25.0)
+    assert tuple(net._last_plan.Pfull) == (7, 7, 7) and net._last_plan.precision == "tf32"
+    xo, *_ = O.forward_t(y, A, B, t, 2, 25.0, True, 1)
+    assert (xr.cpu() - xo).abs().max().item() <= 1e-4
+    ranks, slabs = [], []
+    for r in range(2):
+        den = sharded.ShardedVideoDenoiser(net, tuple(y.shape), r, 2, d, precision="tf32")
+        assert den.plan.precision == "tf32" and tuple(den.plan.Pfull) == (7, 7, 7)
+        ranks.append(den.state)
+        slabs.append(y[:, :, den.geo["f0"]:den.geo["f1"]].contiguous().to(d))
+    xhat, _ = sharded.run_lockstep(ranks, slabs, torch.full((1,), 25.0 / 255.0, device=d))
+    assert (xhat - xr).abs().max().item() <= 1e-4
